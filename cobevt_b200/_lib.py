@@ -1,0 +1,89 @@
+"""ctypes binding of libcobevt_sm100.so (the C ABI declared in include/cobevt_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails the error is
+raised.  The library is built in-tree by ``cobevt_b200/csrc/build.sh`` (see
+``__graft_entry__.build``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcobevt_sm100.so")
+
+c_i32 = ctypes.c_int32
+c_f32 = ctypes.c_float
+c_vp = ctypes.c_void_p
+
+
+class ConvParams(ctypes.Structure):
+    _fields_ = [
+        ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("res", c_vp), ("res32", c_vp),
+        ("y", c_vp), ("y32", c_vp), ("y_ln", c_vp),
+        ("N", c_i32), ("Hin", c_i32), ("Win", c_i32), ("Cin", c_i32),
+        ("OH", c_i32), ("OW", c_i32), ("Cout", c_i32),
+        ("KH", c_i32), ("KW", c_i32), ("stride", c_i32), ("pad", c_i32),
+        ("in_upsample", c_i32), ("act", c_i32), ("dtype", c_i32), ("block_n", c_i32),
+        ("ln_eps", c_f32),
+    ]
+
+
+class TokenMap(ctypes.Structure):
+    _fields_ = [
+        ("views", c_i32), ("H", c_i32), ("W", c_i32), ("Hv", c_i32), ("Wv", c_i32),
+        ("w1", c_i32), ("w2", c_i32), ("grid", c_i32),
+    ]
+
+
+class AttnParams(ctypes.Structure):
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("out", c_vp),
+        ("k_pad", c_vp), ("v_pad", c_vp), ("bias", c_vp), ("key_mask", c_vp),
+        ("qmap", TokenMap), ("kvmap", TokenMap),
+        ("B", c_i32), ("heads", c_i32), ("q_mean", c_i32), ("scale", c_f32), ("dtype", c_i32),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with cobevt_b200/csrc/build.sh "
+                "(or __graft_entry__.build()); there is no fallback path")
+        L = ctypes.CDLL(LIB_PATH)
+        L.cobevt_version.restype = ctypes.c_int
+        L.cobevt_last_error.restype = ctypes.c_char_p
+        L.cobevt_conv_packed_bytes.restype = ctypes.c_int64
+        L.cobevt_conv_packed_bytes.argtypes = [c_i32, c_i32, c_i32]
+        L.cobevt_conv_pack_weight.restype = ctypes.c_int
+        L.cobevt_conv_pack_weight.argtypes = [c_vp, c_i32, c_i32, c_i32, c_vp]
+        L.cobevt_conv2d_nhwc_fwd.restype = ctypes.c_int
+        L.cobevt_conv2d_nhwc_fwd.argtypes = [ctypes.POINTER(ConvParams), c_vp]
+        L.cobevt_window_attn_fwd.restype = ctypes.c_int
+        L.cobevt_window_attn_fwd.argtypes = [ctypes.POINTER(AttnParams), c_vp]
+        for name, argt in _ELTWISE_SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = ctypes.c_int
+            fn.argtypes = argt
+        _lib = L
+    return _lib
+
+
+# element-wise / data-movement entry points: name -> argtypes (see include/cobevt_b200.h)
+_ELTWISE_SIGS = {}
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().cobevt_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (rc={rc}): {msg}")
+
+
+EXPORTED_SYMBOLS = [
+    "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
+    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd",
+]

@@ -1,0 +1,367 @@
+// Windowed / dilated-grid multi-head attention (head_dim = 32) for sm_100a.
+//
+// One CTA (128 threads, one query row per thread) handles one
+// (batch row, window, head, 128-row query tile):
+//   S  = Q K^T          tcgen05.mma  M=128 N=128 K=32   (Q, K: K-major SWIZZLE_64B tiles)
+//   P  = softmax(...)   TMEM -> registers (tcgen05.ld), online max/sum in fp32, exp2 on MUFU,
+//                       P written as 16-bit K-major SWIZZLE_128B A-operand
+//   O += P V            tcgen05.mma  M=128 N=32  K=128  (V: MN-major SWIZZLE_64B, i.e. the
+//                       same row-per-key image as K -- no transpose)
+// Keys/values stream through a double-buffered 128-key chunk; window ('(x w1)(y w2)') and
+// grid ('(w1 x)(w2 y)') partitions are address arithmetic on the NHWC token maps, so none of
+// the reference's rearrange copies exist.  Zero-padded key positions use a constant token
+// (Linear(LayerNorm(0)) of the reference, survey quirk Q2).
+//
+// Reference: CrossWinAttention.forward fax_modules.py:198-248, partitions
+// fax_modules.py:399-433; Attention.forward fax_modules.py:132-176;
+// swap_fusion_modules.Attention.forward :87-128.
+#include "sm100.cuh"
+#include "common.h"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int TILE_Q = 128;
+constexpr int CHUNK = 128;   // keys per chunk
+constexpr int DH = 32;       // head dim
+constexpr int SQ_BYTES = TILE_Q * DH * 2;        // 8 KB
+constexpr int SK_BYTES = CHUNK * DH * 2;         // 8 KB
+constexpr int SP_BYTES = TILE_Q * CHUNK * 2;     // 32 KB
+constexpr int SMEM_BYTES = 1024 + SQ_BYTES + 2 * (2 * SK_BYTES) + SP_BYTES;
+constexpr int TMEM_COLS = 256;  // S: [0,128)  O: [128,160)
+
+struct AArgs {
+  CobevtAttnParams p;
+  int32_t n_win, q_tiles, Lq, Lk, n_chunks, q_passes, C;
+  int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
+  uint32_t idesc_qk, idesc_pv;
+};
+
+struct Tok {
+  int n, py, px;
+  bool in_range;  // inside the valid (stored) extent
+};
+
+// token t (0 .. views*w1*w2) of window `win` -> plane / pixel
+__device__ __forceinline__ Tok token_of(const CobevtTokenMap& m, int nx, int ny, int win, int t) {
+  Tok r;
+  const int ww = m.w1 * m.w2;
+  r.n = t / ww;
+  const int tt = t - r.n * ww;
+  const int i = tt / m.w2, j = tt - i * m.w2;
+  const int X = win / ny, Y = win - X * ny;
+  if (m.grid) {
+    r.py = i * nx + X;
+    r.px = j * ny + Y;
+  } else {
+    r.py = X * m.w1 + i;
+    r.px = Y * m.w2 + j;
+  }
+  r.in_range = r.py < m.Hv && r.px < m.Wv;
+  return r;
+}
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sKV = smem + SQ_BYTES;              // buffer b: K at sKV + b*2*SK_BYTES, V right after
+  uint8_t* sP = sKV + 4 * SK_BYTES;
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_base_s;
+
+  const CobevtAttnParams& p = a.p;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  int item = blockIdx.x;
+  const int q_tile = item % a.q_tiles; item /= a.q_tiles;
+  const int head = item % p.heads;     item /= p.heads;
+  const int win = item % a.n_win;
+  const int b = item / a.n_win;
+  const int C = a.C;
+  const int bf16 = p.dtype;
+
+  if (tid == 0) {
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16);
+  uint32_t ph_s = 0, ph_o = 0;
+
+  const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q);
+  const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
+  const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
+  const float sl2 = p.scale * 1.4426950408889634f;
+
+  // my query row
+  const int qrow = q_tile * TILE_Q + tid;      // index inside the window's row list
+  const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
+  const bool row_ok = qrow < rows_per_pass;
+
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+
+  // issue the cp.async loads of KV chunk `c` into buffer `buf`
+  auto load_kv = [&](int c, int buf) {
+    const int key = c * CHUNK + tid;
+    uint8_t* dK = sKV + buf * 2 * SK_BYTES;
+    uint8_t* dV = dK + SK_BYTES;
+    const uint8_t* srcK = kb_;
+    const uint8_t* srcV = vb_;
+    uint32_t nb = 0;
+    if (key < a.Lk) {
+      const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, key);
+      if (t.in_range) {
+        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * C + head * DH;
+        srcK = kb_ + off * 2;
+        srcV = vb_ + off * 2;
+        nb = 16;
+      } else if (p.k_pad) {
+        srcK = reinterpret_cast<const uint8_t*>(p.k_pad) + head * DH * 2;
+        srcV = reinterpret_cast<const uint8_t*>(p.v_pad) + head * DH * 2;
+        nb = 16;
+      }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      cp_async16(dK + sw64_off(tid, ch), srcK + (nb ? ch * 16 : 0), nb);
+      cp_async16(dV + sw64_off(tid, ch), srcV + (nb ? ch * 16 : 0), nb);
+    }
+    cp_async_commit();
+  };
+
+  for (int pass = 0; pass < a.q_passes; ++pass) {
+    // ---- Q tile ------------------------------------------------------------
+    {
+      const uint8_t* src = qb;
+      uint32_t nb = 0;
+      if (row_ok) {
+        const int t_idx = p.q_mean ? pass * rows_per_pass + qrow : qrow;
+        const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, t_idx);
+        const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
+        src = qb + off * 2;
+        nb = 16;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) cp_async16(sQ + sw64_off(tid, ch), src + (nb ? ch * 16 : 0), nb);
+      cp_async_commit();
+    }
+    load_kv(0, 0);
+
+    float m_run = -INFINITY, l_run = 0.f;
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+
+    for (int c = 0; c < a.n_chunks; ++c) {
+      const int buf = c & 1;
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncthreads();
+      // ---- S = Q K^T ----------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(sQ);
+        const uint32_t sb = smem_u32(sKV + buf * 2 * SK_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks) {
+          const uint64_t da = make_smem_desc(sa + ks * 32, 16, 512, LAYOUT_SW64);
+          const uint64_t db = make_smem_desc(sb + ks * 32, 16, 512, LAYOUT_SW64);
+          umma_f16(tmem_base, da, db, a.idesc_qk, ks ? 1u : 0u);
+        }
+        umma_commit(&bar_s);
+      }
+      // prefetch next chunk into the other buffer (its previous user, chunk c-1, has retired)
+      if (c + 1 < a.n_chunks) load_kv(c + 1, buf ^ 1);
+
+      mbar_wait(&bar_s, ph_s);
+      ph_s ^= 1;
+      tc_fence_after_sync();
+
+      // ---- softmax on this row (two sweeps over the TMEM row: max, then exp) ------
+      const int key0 = c * CHUNK;
+      auto logits = [&](int g, float (&x)[32]) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + g * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * sl2;
+        const int kg = key0 + g * 32;
+        if (p.bias && row_ok) {
+          const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + kg;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kg + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
+        }
+        if (p.key_mask) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (kg + j < a.Lk) {
+              const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, kg + j);
+              const uint8_t mk = p.key_mask[(((int64_t)b * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kvmap.views + t.n];
+              if (mk == 0) x[j] = -INFINITY;
+            }
+          }
+        }
+        if (kg + 32 > a.Lk) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (kg + j >= a.Lk) x[j] = -INFINITY;
+        }
+      };
+      float mx = m_run;
+#pragma unroll 1
+      for (int g = 0; g < CHUNK / 32; ++g) {
+        float x[32];
+        logits(g, x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
+      }
+      const float m_safe = (mx == -INFINITY) ? 0.f : mx;
+      const float alpha = fast_exp2(m_run - m_safe);
+      float sum = 0.f;
+#pragma unroll 1
+      for (int g = 0; g < CHUNK / 32; ++g) {
+        float x[32];
+        logits(g, x);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          x[j] = fast_exp2(x[j] - m_safe);
+          sum += x[j];
+        }
+        // P -> smem (A operand, two 64-key SW128 halves); this group = 4 x 16-byte chunks
+        uint8_t* dst = sP + (g >> 1) * (TILE_Q * 128);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          uint4 u;
+          u.x = pack_h2(x[cc * 8 + 0], x[cc * 8 + 1], bf16);
+          u.y = pack_h2(x[cc * 8 + 2], x[cc * 8 + 3], bf16);
+          u.z = pack_h2(x[cc * 8 + 4], x[cc * 8 + 5], bf16);
+          u.w = pack_h2(x[cc * 8 + 6], x[cc * 8 + 7], bf16);
+          *reinterpret_cast<uint4*>(dst + sw128_off(tid, (g & 1) * 4 + cc)) = u;
+        }
+      }
+      l_run = l_run * alpha + sum;
+      m_run = mx;
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      __syncthreads();
+      // ---- O_c = P V -------------------------------------------------------------
+      if (tid == 0) {
+        tc_fence_after_sync();
+        const uint32_t sa = smem_u32(sP);
+        const uint32_t sv = smem_u32(sKV + buf * 2 * SK_BYTES + SK_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < CHUNK / 16; ++ks) {
+          const uint64_t da = make_smem_desc(sa + (ks >> 2) * (TILE_Q * 128) + (ks & 3) * 32, 16, 1024, LAYOUT_SW128);
+          const uint64_t db = make_smem_desc(sv + ks * 16 * 64, 512, 512, LAYOUT_SW64);
+          umma_f16(tmem_base + CHUNK, da, db, a.idesc_pv, ks ? 1u : 0u);
+        }
+        umma_commit(&bar_o);
+      }
+      mbar_wait(&bar_o, ph_o);
+      ph_o ^= 1;
+      tc_fence_after_sync();
+      {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + CHUNK, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(r[d]));
+      }
+      tc_fence_before_sync();
+    }
+    const float inv = (l_run > 0.f) ? 1.0f / (l_run * (float)a.q_passes) : 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
+    __syncthreads();  // all reads of sQ / KV buffers by the tensor core are complete (bar_o)
+  }
+
+  // ---- write the row --------------------------------------------------------------
+  if (row_ok) {
+    const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
+    int64_t off;
+    if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
+    else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
+    uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      uint4 u;
+      u.x = pack_h2(acc[ch * 8 + 0], acc[ch * 8 + 1], bf16);
+      u.y = pack_h2(acc[ch * 8 + 2], acc[ch * 8 + 3], bf16);
+      u.z = pack_h2(acc[ch * 8 + 4], acc[ch * 8 + 5], bf16);
+      u.w = pack_h2(acc[ch * 8 + 6], acc[ch * 8 + 7], bf16);
+      *reinterpret_cast<uint4*>(op + ch * 16) = u;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace
+
+extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
+  if (!p || !p->q || !p->k || !p->v || !p->out) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: null pointer");
+  const CobevtTokenMap& qm = p->qmap;
+  const CobevtTokenMap& km = p->kvmap;
+  if (qm.w1 <= 0 || qm.w2 <= 0 || km.w1 <= 0 || km.w2 <= 0 || qm.H % qm.w1 || qm.W % qm.w2 || km.H % km.w1 || km.W % km.w2)
+    return cobevt::fail(COBEVT_ERR_SHAPE, "attn: map extents not divisible by the window");
+  if (qm.Hv != qm.H || qm.Wv != qm.W) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: padded query maps are not supported");
+  if (km.Hv > km.H || km.Wv > km.W) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: valid extent exceeds padded extent");
+  if ((p->k_pad == nullptr) != (p->v_pad == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: k_pad/v_pad must come together");
+  AArgs a;
+  a.p = *p;
+  a.q_nx = qm.H / qm.w1; a.q_ny = qm.W / qm.w2;
+  a.k_nx = km.H / km.w1; a.k_ny = km.W / km.w2;
+  a.n_win = a.q_nx * a.q_ny;
+  if (a.n_win != a.k_nx * a.k_ny)
+    return cobevt::fail(COBEVT_ERR_SHAPE, "attn: %d query windows vs %d key windows", a.n_win, a.k_nx * a.k_ny);
+  a.Lq = qm.views * qm.w1 * qm.w2;
+  a.Lk = km.views * km.w1 * km.w2;
+  a.n_chunks = cobevt::ceil_div(a.Lk, CHUNK);
+  a.q_passes = p->q_mean ? qm.views : 1;
+  const int rows = p->q_mean ? qm.w1 * qm.w2 : a.Lq;
+  a.q_tiles = cobevt::ceil_div(rows, TILE_Q);
+  a.C = p->heads * DH;
+  if (p->bias && p->q_mean) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias with q_mean");
+  if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: dtype");
+  const bool bf = p->dtype == COBEVT_BF16;
+  a.idesc_qk = make_idesc_f16(128, CHUNK, bf, false, false);
+  a.idesc_pv = make_idesc_f16(128, DH, bf, false, true);
+  const int64_t items = (int64_t)p->B * a.n_win * p->heads * a.q_tiles;
+  if (items <= 0 || items > 0x7fffffff) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bad grid");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  window_attn_kernel<<<(unsigned)items, 128, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return cobevt::check_launch("window_attn_kernel");
+}

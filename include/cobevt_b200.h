@@ -1,0 +1,115 @@
+/*
+ * cobevt_b200.h -- C ABI of libcobevt_sm100.so (sm_100a only).
+ *
+ * The reference (DerrickXuNu/CoBEVT) has no FFI layer: its operator API is the
+ * PyTorch nn.Module surface.  These entry points are what the Python mirror
+ * modules in cobevt_b200/ bind through ctypes; each one names the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions (all entry points):
+ *   - plain pointers + sizes, no torch types; all pointers are DEVICE pointers
+ *     unless stated; activations are NHWC ("tokens x channels") 16-bit floats
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work, they
+ *     never synchronise and never allocate device memory
+ *   - return 0 on success, <0 on error: -1 bad shape/argument, -2 unsupported
+ *     configuration, -3 CUDA error; cobevt_last_error() returns the message
+ *   - dtype: 0 = fp16, 1 = bf16 (16-bit storage, fp32 accumulation)
+ */
+#ifndef COBEVT_B200_H_
+#define COBEVT_B200_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define COBEVT_OK 0
+#define COBEVT_ERR_SHAPE (-1)
+#define COBEVT_ERR_UNSUPPORTED (-2)
+#define COBEVT_ERR_CUDA (-3)
+
+enum { COBEVT_F16 = 0, COBEVT_BF16 = 1 };
+enum { COBEVT_ACT_NONE = 0, COBEVT_ACT_RELU = 1, COBEVT_ACT_GELU = 2 };
+
+int cobevt_version(void);
+const char* cobevt_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * Implicit-GEMM convolution / token GEMM on tcgen05 tensor cores.
+ *   y[m, co] = act( sum_{ky,kx,ci} x[pix(m)+(ky,kx), ci] * w[co, ky, kx, ci]
+ *                   + bias[co] + res[m, co] )
+ * Replaces: torchvision ResNet convs + BN + ReLU + residual used by
+ *   opv2v/opencood/models/backbones/resnet_ms.py:46-89, the Bottleneck /
+ *   downsample convs of sub_modules/fax_modules.py:472-489, every nn.Linear on
+ *   the token path (fax_modules.py:189-193,311-312; swap_fusion_modules.py:45-53;
+ *   base_transformer.py:112-124), naive_decoder.py:62-91, bev_seg_head.py:35-61.
+ * A 1x1 "conv" over a (rows,1,1,C) tensor is a plain GEMM.
+ * -------------------------------------------------------------------------*/
+typedef struct {
+  const void* x;       /* (N, Hin, Win, Cin) 16-bit, Cin % 8 == 0                     */
+  const void* w;       /* packed by cobevt_conv_pack_weight                           */
+  const float* bias;   /* [Cout] fp32 or NULL                                         */
+  const void* res;     /* (M, Cout) 16-bit residual added before act, or NULL         */
+  const float* res32;  /* (M, Cout) fp32 residual, or NULL                            */
+  void* y;             /* (M, Cout) 16-bit output or NULL                             */
+  float* y32;          /* (M, Cout) fp32 output or NULL                               */
+  void* y_ln;          /* (M, Cout) 16-bit LayerNorm-normalised copy (no affine) or NULL;
+                          requires Cout == block_n == 128                             */
+  int32_t N, Hin, Win, Cin; /* physical input extents                                  */
+  int32_t OH, OW, Cout;     /* M = N*OH*OW                                             */
+  int32_t KH, KW, stride, pad;
+  int32_t in_upsample; /* 1: logical input is the physical one nearest-upsampled x2    */
+  int32_t act;         /* COBEVT_ACT_*                                                 */
+  int32_t dtype;       /* COBEVT_F16 / COBEVT_BF16                                     */
+  int32_t block_n;     /* N tile the weights were packed for: 16,32,64,128,256         */
+  float ln_eps;
+} CobevtConvParams;
+
+/* bytes of the packed weight buffer for (Cout, KH*KW*Cin, block_n) */
+int64_t cobevt_conv_packed_bytes(int32_t Cout, int32_t K, int32_t block_n);
+/* HOST-side pack: w_host is [Cout][K] row-major 16-bit (K = KH*KW*Cin, ci fastest);
+ * out_host receives the tile images the kernel bulk-copies (SWIZZLE_128B K-major). */
+int cobevt_conv_pack_weight(const uint16_t* w_host, int32_t Cout, int32_t K, int32_t block_n,
+                            uint16_t* out_host);
+int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * Windowed / dilated-grid multi-head attention (head_dim 32) on tcgen05:
+ *   S = scale * Q K^T (+ bias) (+ key mask) ; P = softmax(S) ; O = P V
+ * Q, K, V are already projected token maps; window / grid partitions are pure
+ * addressing (no rearranged copies).
+ * Replaces: CrossWinAttention.forward fax_modules.py:198-248 (core :226-234) with
+ *   the partitions of CrossViewSwapAttention.forward :399-433; Attention.forward
+ *   fax_modules.py:132-176; swap_fusion_modules.Attention.forward :87-128.
+ * -------------------------------------------------------------------------*/
+typedef struct {
+  int32_t views;      /* token planes per batch row (cameras / agents)                */
+  int32_t H, W;       /* logical (padded) map extent the partition is defined on      */
+  int32_t Hv, Wv;     /* valid extent stored in memory (<= H, W); outside = pad token */
+  int32_t w1, w2;     /* window extent                                                */
+  int32_t grid;       /* 0: window partition '(x w1) (y w2)'; 1: grid '(w1 x) (w2 y)' */
+} CobevtTokenMap;
+
+typedef struct {
+  const void* q;      /* (B, q.views, q.Hv, q.Wv, C) 16-bit, C = heads*32            */
+  const void* k;      /* (B, kv.views, kv.Hv, kv.Wv, C)                              */
+  const void* v;
+  void* out;          /* q_mean ? (B, q.Hv, q.Wv, C) : (B, q.views, q.Hv, q.Wv, C)   */
+  const void* k_pad;  /* [C] 16-bit token used for padded key positions, or NULL     */
+  const void* v_pad;
+  const float* bias;  /* (heads, Lq, Lk) fp32 additive bias or NULL                  */
+  const uint8_t* key_mask; /* (B, kv.Hv, kv.Wv, kv.views) 1 = keep, 0 = -inf; or NULL */
+  CobevtTokenMap qmap, kvmap;
+  int32_t B, heads;
+  int32_t q_mean;     /* 1: q views are separate passes averaged (CrossWinAttention
+                         mean over n, fax_modules.py:243); 0: views are extra rows   */
+  float scale;
+  int32_t dtype;
+} CobevtAttnParams;
+
+int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COBEVT_B200_H_ */
