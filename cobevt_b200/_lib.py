@@ -18,10 +18,11 @@ c_vp = ctypes.c_void_p
 class ConvParams(ctypes.Structure):
     _fields_ = [
         ("x", c_vp), ("w", c_vp), ("bias", c_vp), ("res", c_vp), ("res32", c_vp),
-        ("y", c_vp), ("y32", c_vp), ("y_ln", c_vp),
+        ("y", c_vp), ("y32", c_vp), ("y_ln", c_vp), ("ln_gamma", c_vp), ("ln_beta", c_vp),
         ("N", c_i32), ("Hin", c_i32), ("Win", c_i32), ("Cin", c_i32),
         ("OH", c_i32), ("OW", c_i32), ("Cout", c_i32),
-        ("KH", c_i32), ("KW", c_i32), ("stride", c_i32), ("pad", c_i32),
+        ("KH", c_i32), ("KW", c_i32),
+        ("stride_h", c_i32), ("stride_w", c_i32), ("pad_h", c_i32), ("pad_w", c_i32), ("res_rows", c_i32),
         ("in_upsample", c_i32), ("act", c_i32), ("dtype", c_i32), ("block_n", c_i32),
         ("ln_eps", c_f32),
     ]
@@ -39,7 +40,8 @@ class AttnParams(ctypes.Structure):
         ("q", c_vp), ("k", c_vp), ("v", c_vp), ("out", c_vp),
         ("k_pad", c_vp), ("v_pad", c_vp), ("bias", c_vp), ("key_mask", c_vp),
         ("qmap", TokenMap), ("kvmap", TokenMap),
-        ("B", c_i32), ("heads", c_i32), ("q_mean", c_i32), ("scale", c_f32), ("dtype", c_i32),
+        ("B", c_i32), ("heads", c_i32),
+        ("q_stride", c_i32), ("kv_stride", c_i32), ("out_stride", c_i32), ("q_mean", c_i32), ("scale", c_f32), ("dtype", c_i32),
     ]
 
 
@@ -74,7 +76,18 @@ def lib():
 
 
 # element-wise / data-movement entry points: name -> argtypes (see include/cobevt_b200.h)
-_ELTWISE_SIGS = {}
+c_i64 = ctypes.c_int64
+_ELTWISE_SIGS = {
+    "cobevt_pack_rgb8": [c_vp, c_vp, c_i64, c_i32, c_vp],
+    "cobevt_maxpool3x3s2_nhwc": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_bn_relu2": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
+    "cobevt_ray_embed": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_bev_query": [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
+    "cobevt_layernorm_rows": [c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_f32, c_i32, c_vp],
+    "cobevt_mean_views_ln": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
+    "cobevt_sttf_regroup": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_vp],
+    "cobevt_permute": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+}
 
 
 def check(rc, what):
@@ -86,4 +99,4 @@ def check(rc, what):
 EXPORTED_SYMBOLS = [
     "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
     "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd",
-]
+] + list(_ELTWISE_SIGS)

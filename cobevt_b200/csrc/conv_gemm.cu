@@ -120,8 +120,8 @@ conv_gemm_kernel(const KArgs a) {
     const int rem = mm - n * ohw;
     const int oy = rem / p.OW, ox = rem - oy * p.OW;
     ri.pixbase = n * p.Hin * p.Win;
-    ri.iy0 = oy * p.stride - p.pad;
-    ri.ix0 = ox * p.stride - p.pad;
+    ri.iy0 = oy * p.stride_h - p.pad_h;
+    ri.ix0 = ox * p.stride_w - p.pad_w;
     rows[tid] = ri;
   }
   for (int q = tid; q < KB * 8; q += NUM_THREADS) {
@@ -248,8 +248,9 @@ conv_gemm_kernel(const KArgs a) {
 #pragma unroll
           for (int j = 0; j < G; ++j) if (n0 + j < p.Cout) v[j] += __ldg(p.bias + n0 + j);
         }
+        const int64_t mr = p.res_rows > 0 ? (m % p.res_rows) : m;
         if (p.res) {
-          const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (m * p.Cout + n0) * 2;
+          const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
 #pragma unroll
           for (int j = 0; j < G; j += 8) {
             if (n0 + j + 8 <= p.Cout) {
@@ -265,7 +266,7 @@ conv_gemm_kernel(const KArgs a) {
           }
         }
         if (p.res32) {
-          const float* rp = p.res32 + m * p.Cout + n0;
+          const float* rp = p.res32 + mr * p.Cout + n0;
 #pragma unroll
           for (int j = 0; j < G; j += 4) {
             if (n0 + j + 4 <= p.Cout) {
@@ -325,12 +326,18 @@ conv_gemm_kernel(const KArgs a) {
         } else {
           uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
 #pragma unroll
+          for (int j = 0; j < G; ++j) v[j] = (v[j] - mean) * rstd;
+          if (p.ln_gamma) {
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = fmaf(v[j], __ldg(p.ln_gamma + n0 + j), __ldg(p.ln_beta + n0 + j));
+          }
+#pragma unroll
           for (int j = 0; j < G; j += 8) {
             uint4 u;
-            u.x = pack2((v[j] - mean) * rstd, (v[j + 1] - mean) * rstd, bf16);
-            u.y = pack2((v[j + 2] - mean) * rstd, (v[j + 3] - mean) * rstd, bf16);
-            u.z = pack2((v[j + 4] - mean) * rstd, (v[j + 5] - mean) * rstd, bf16);
-            u.w = pack2((v[j + 6] - mean) * rstd, (v[j + 7] - mean) * rstd, bf16);
+            u.x = pack2(v[j], v[j + 1], bf16);
+            u.y = pack2(v[j + 2], v[j + 3], bf16);
+            u.z = pack2(v[j + 4], v[j + 5], bf16);
+            u.w = pack2(v[j + 6], v[j + 7], bf16);
             *reinterpret_cast<uint4*>(yp + j * 2) = u;
           }
         }
@@ -404,12 +411,13 @@ extern "C" int cobevt_conv_pack_weight(const uint16_t* w, int32_t Cout, int32_t 
 extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
   if (!p || !p->x || !p->w) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: null pointer");
   if (p->Cin % 8 != 0) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: Cin %d not a multiple of 8", p->Cin);
-  if (p->N <= 0 || p->OH <= 0 || p->OW <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 || p->stride <= 0)
+  if (p->N <= 0 || p->OH <= 0 || p->OW <= 0 || p->Cout <= 0 || p->KH <= 0 || p->KW <= 0 || p->stride_h <= 0 || p->stride_w <= 0)
     return cobevt::fail(COBEVT_ERR_SHAPE, "conv: bad extents");
   if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: dtype %d", p->dtype);
   if (!p->y && !p->y32 && !p->y_ln) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: no output");
   if (p->y_ln && !(p->Cout == 128 && p->block_n == 128))
     return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: y_ln needs Cout == block_n == 128");
+  if ((p->ln_gamma == nullptr) != (p->ln_beta == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: ln_gamma/ln_beta must come together");
   if (p->Cout % 8 != 0 && (p->res || p->y_ln)) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %% 8 with res/ln");
   const int64_t M64 = (int64_t)p->N * p->OH * p->OW;
   if (M64 > (1ll << 30)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: M too large");

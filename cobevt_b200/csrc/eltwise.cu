@@ -1,0 +1,459 @@
+// HBM-bound element-wise / gather kernels of the FAX path (coalesced 8/16-byte accesses,
+// one warp per token row where a row reduction is needed).  Each entry point cites the
+// reference lines it replaces; see include/cobevt_b200.h.
+#include "common.h"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace {
+
+__device__ __forceinline__ float2 up2(uint32_t u, int bf16) {
+  if (bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+__device__ __forceinline__ uint32_t pk2(float a, float b, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint16_t pk1(float a, int bf16) { return (uint16_t)(pk2(a, 0.f, bf16) & 0xFFFFu); }
+__device__ __forceinline__ float up1(uint16_t u, int bf16) { return up2((uint32_t)u, bf16).x; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int MAXC_PER_LANE = 8;  // rows up to 256 channels per warp
+
+// load C/32 consecutive channels of a 16-bit row for this lane (C % 64 == 0 -> pairs)
+__device__ __forceinline__ void load_row(const uint16_t* row, int C, int lane, int bf16, float* v) {
+  const int per = C / 32;  // 2, 4 or 8
+  const uint16_t* p = row + lane * per;
+  if (per == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(p);
+    float2 a = up2(u.x, bf16), b = up2(u.y, bf16);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  } else if (per == 8) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 a = up2(u.x, bf16), b = up2(u.y, bf16), c = up2(u.z, bf16), d = up2(u.w, bf16);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
+  } else {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
+    float2 a = up2(u, bf16);
+    v[0] = a.x; v[1] = a.y;
+  }
+}
+__device__ __forceinline__ void store_row(uint16_t* row, int C, int lane, int bf16, const float* v) {
+  const int per = C / 32;
+  uint16_t* p = row + lane * per;
+  if (per == 4) {
+    uint2 u; u.x = pk2(v[0], v[1], bf16); u.y = pk2(v[2], v[3], bf16);
+    *reinterpret_cast<uint2*>(p) = u;
+  } else if (per == 8) {
+    uint4 u; u.x = pk2(v[0], v[1], bf16); u.y = pk2(v[2], v[3], bf16); u.z = pk2(v[4], v[5], bf16); u.w = pk2(v[6], v[7], bf16);
+    *reinterpret_cast<uint4*>(p) = u;
+  } else {
+    *reinterpret_cast<uint32_t*>(p) = pk2(v[0], v[1], bf16);
+  }
+}
+
+// normalise a row held across the warp: (v - mean) * rstd [* gamma + beta]
+__device__ __forceinline__ void ln_row(float* v, int per, int C, int lane, float eps, const float* gamma, const float* beta) {
+  float s = 0.f;
+  for (int i = 0; i < per; ++i) s += v[i];
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+  for (int i = 0; i < per; ++i) { const float d = v[i] - mean; q += d * d; }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  for (int i = 0; i < per; ++i) {
+    float o = (v[i] - mean) * rstd;
+    if (gamma) o = fmaf(o, gamma[lane * per + i], beta[lane * per + i]);
+    v[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------ pack_rgb8
+__global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int64_t npix, int bf16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float r = x[i * 3], g = x[i * 3 + 1], b = x[i * 3 + 2];
+  uint4 u;
+  u.x = pk2(r, g, bf16); u.y = pk2(b, 0.f, bf16); u.z = 0; u.w = 0;
+  *reinterpret_cast<uint4*>(y + i * 8) = u;
+}
+
+// ------------------------------------------------------------------ maxpool 3x3 s2 p1
+__global__ void maxpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int C,
+                               int OH, int OW, int bf16) {
+  const int cg = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)N * OH * OW * cg;
+  if (idx >= total) return;
+  const int c8 = (int)(idx % cg);
+  int64_t t = idx / cg;
+  const int ox = (int)(t % OW); t /= OW;
+  const int oy = (int)(t % OH);
+  const int n = (int)(t / OH);
+  float m[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    if (iy < 0 || iy >= H) continue;
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - 1 + kx;
+      if (ix < 0 || ix >= W) continue;
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + iy) * W + ix) * C + c8 * 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = up2(w4[j], bf16);
+        m[2 * j] = fmaxf(m[2 * j], f.x);
+        m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+      }
+    }
+  }
+  uint4 o;
+  o.x = pk2(m[0], m[1], bf16); o.y = pk2(m[2], m[3], bf16); o.z = pk2(m[4], m[5], bf16); o.w = pk2(m[6], m[7], bf16);
+  *reinterpret_cast<uint4*>(y + (((int64_t)n * OH + oy) * OW + ox) * C + c8 * 8) = o;
+}
+
+// ------------------------------------------------------------------ y = relu(x*s + b), two affine sets
+__global__ void bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ sa, const float* __restrict__ ba,
+                                uint16_t* __restrict__ ya, const float* __restrict__ sb, const float* __restrict__ bb,
+                                uint16_t* __restrict__ yb, int64_t rows, int C, int bf16) {
+  const int cg = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cg) return;
+  const int c0 = (int)(idx % cg) * 8;
+  const uint4 u = *reinterpret_cast<const uint4*>(x + idx * 8);
+  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { const float2 f = up2(w4[j], bf16); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+  float o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], sa[c0 + j], ba[c0 + j]), 0.f);
+  uint4 w;
+  w.x = pk2(o[0], o[1], bf16); w.y = pk2(o[2], o[3], bf16); w.z = pk2(o[4], o[5], bf16); w.w = pk2(o[6], o[7], bf16);
+  *reinterpret_cast<uint4*>(ya + idx * 8) = w;
+  if (yb) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], sb[c0 + j], bb[c0 + j]), 0.f);
+    w.x = pk2(o[0], o[1], bf16); w.y = pk2(o[2], o[3], bf16); w.z = pk2(o[4], o[5], bf16); w.w = pk2(o[6], o[7], bf16);
+    *reinterpret_cast<uint4*>(yb + idx * 8) = w;
+  }
+}
+
+// ------------------------------------------------------------------ ray-direction embedding
+// one warp per feature cell; out = normalize(W_img d - W_cam c)   (fax_modules.py:346-358)
+__global__ void ray_embed_kernel(const float* __restrict__ I_inv, const float* __restrict__ E_inv,
+                                 const float* __restrict__ w_img, const float* __restrict__ w_cam,
+                                 uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
+                                 int C, int invert_I, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cell >= (int64_t)NV * h * w) return;
+  const int ix = (int)(cell % w);
+  const int iy = (int)((cell / w) % h);
+  const int v = (int)(cell / ((int64_t)w * h));
+  const float px = (w > 1 ? (float)ix / (float)(w - 1) : 0.f) * image_w;
+  const float py = (h > 1 ? (float)iy / (float)(h - 1) : 0.f) * image_h;
+  float Ii[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) Ii[r] = I_inv[v * 9 + r];
+  if (invert_I) {   // batch['intrinsic'].inverse(), fax_modules.py:500-501 (adjugate / determinant)
+    const float a = Ii[0], b_ = Ii[1], c_ = Ii[2], d_ = Ii[3], e_ = Ii[4], f = Ii[5], g = Ii[6], hh = Ii[7], k = Ii[8];
+    const float A = e_ * k - f * hh, B = -(d_ * k - f * g), Cc = d_ * hh - e_ * g;
+    const float idet = 1.0f / (a * A + b_ * B + c_ * Cc);
+    Ii[0] = A * idet;  Ii[1] = -(b_ * k - c_ * hh) * idet; Ii[2] = (b_ * f - c_ * e_) * idet;
+    Ii[3] = B * idet;  Ii[4] = (a * k - c_ * g) * idet;    Ii[5] = -(a * f - c_ * d_) * idet;
+    Ii[6] = Cc * idet; Ii[7] = -(a * hh - b_ * g) * idet;  Ii[8] = (a * e_ - b_ * d_) * idet;
+  }
+  const float* Ei = E_inv + v * 16;
+  const float cx = Ii[0] * px + Ii[1] * py + Ii[2];
+  const float cy = Ii[3] * px + Ii[4] * py + Ii[5];
+  const float cz = Ii[6] * px + Ii[7] * py + Ii[8];
+  float d[4], c[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    d[r] = Ei[r * 4] * cx + Ei[r * 4 + 1] * cy + Ei[r * 4 + 2] * cz + Ei[r * 4 + 3];
+    c[r] = Ei[r * 4 + 3];
+  }
+  const int per = C / 32;
+  float e[MAXC_PER_LANE];
+  float ss = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const int ch = lane * per + i;
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a += w_img[ch * 4 + r] * d[r] - w_cam[ch * 4 + r] * c[r];
+    e[i] = a;
+    ss += a * a;
+  }
+  const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
+  for (int i = 0; i < per; ++i) e[i] *= inv;
+  store_row(out + cell * C, C, lane, bf16, e);
+}
+
+// ------------------------------------------------------------------ BEV positional query
+// out[b, n, p, :] = LN0( x[b, p, :] + normalize(W_bev world_p + b_bev - W_cam c_{b,n}) )
+// (fax_modules.py:370-375,387-390 followed by the LayerNorm of to_q, :189,216)
+__global__ void bev_query_kernel(const uint16_t* __restrict__ x, int64_t x_rows, const float* __restrict__ world,
+                                 const float* __restrict__ w_bev, const float* __restrict__ b_bev,
+                                 const float* __restrict__ w_cam, const float* __restrict__ E_inv,
+                                 uint16_t* __restrict__ out, int BL, int n, int P, int C, float eps, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= (int64_t)BL * n * P) return;
+  const int p = (int)(row % P);
+  const int v = (int)(row / P);        // b * n + view
+  const int b = v / n;
+  const float wx = world[p], wy = world[P + p];
+  const float* Ei = E_inv + (int64_t)v * 16;
+  const float c0 = Ei[3], c1 = Ei[7], c2 = Ei[11], c3 = Ei[15];
+  const int per = C / 32;
+  float e[MAXC_PER_LANE], xv[MAXC_PER_LANE];
+  float ss = 0.f;
+  for (int i = 0; i < per; ++i) {
+    const int ch = lane * per + i;
+    const float a = w_bev[ch * 2] * wx + w_bev[ch * 2 + 1] * wy + b_bev[ch] -
+                    (w_cam[ch * 4] * c0 + w_cam[ch * 4 + 1] * c1 + w_cam[ch * 4 + 2] * c2 + w_cam[ch * 4 + 3] * c3);
+    e[i] = a;
+    ss += a * a;
+  }
+  const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
+  const int64_t xr = ((int64_t)b * P + p) % x_rows;
+  load_row(x + xr * C, C, lane, bf16, xv);
+  for (int i = 0; i < per; ++i) e[i] = fmaf(e[i], inv, xv[i]);
+  ln_row(e, per, C, lane, eps, nullptr, nullptr);
+  store_row(out + row * C, C, lane, bf16, e);
+}
+
+// ------------------------------------------------------------------ LayerNorm over rows
+__global__ void layernorm_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, uint16_t* __restrict__ y, int64_t rows, int C,
+                                 float eps, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float v[MAXC_PER_LANE];
+  load_row(x + row * C, C, lane, bf16, v);
+  ln_row(v, C / 32, C, lane, eps, gamma, beta);
+  store_row(y + row * C, C, lane, bf16, v);
+}
+
+// ------------------------------------------------------------------ mean over views + LayerNorm
+// x (B, L, P, C) -> y (B, P, C) = LN0(mean_l x)   (swap_fusion_modules.py:275-278)
+__global__ void mean_views_ln_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int L, int P,
+                                     int C, float eps, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= (int64_t)B * P) return;
+  const int p = (int)(row % P);
+  const int b = (int)(row / P);
+  const int per = C / 32;
+  float acc[MAXC_PER_LANE];
+  for (int i = 0; i < per; ++i) acc[i] = 0.f;
+  for (int l = 0; l < L; ++l) {
+    float v[MAXC_PER_LANE];
+    load_row(x + (((int64_t)b * L + l) * P + p) * C, C, lane, bf16, v);
+    for (int i = 0; i < per; ++i) acc[i] += v[i];
+  }
+  const float invL = 1.0f / (float)L;
+  for (int i = 0; i < per; ++i) acc[i] *= invL;
+  ln_row(acc, per, C, lane, eps, nullptr, nullptr);
+  store_row(y + row * C, C, lane, bf16, acc);
+}
+
+// ------------------------------------------------------------------ regroup + STTF warp + ROI mask
+// One warp per (b, l, h, w) output cell.  Restates corpbevt.py:28-64 (transpose, flip, affine
+// warp about the map centre, flip, transpose) directly in (h, w) index space, fuse_utils.py:8-61
+// (regroup: row prefix[b] + l, zero rows beyond record_len) and
+// torch_transformation_utils.py:11-49 (nearest-warped ROI x cav mask).
+__global__ void sttf_kernel(const uint16_t* __restrict__ x, const float* __restrict__ tm,
+                            const int64_t* __restrict__ record_len, uint16_t* __restrict__ out,
+                            uint8_t* __restrict__ mask, int B, int L, int H, int W, int C, float inv_disc,
+                            int use_roi, int bf16) {
+  const int lane = threadIdx.x & 31;
+  const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (cell >= (int64_t)B * L * H * W) return;
+  const int w = (int)(cell % W);
+  const int h = (int)((cell / W) % H);
+  const int l = (int)((cell / ((int64_t)W * H)) % L);
+  const int b = (int)(cell / ((int64_t)W * H * L));
+  int64_t start = 0;
+  for (int i = 0; i < b; ++i) start += record_len[i];
+  const int len = (int)record_len[b];
+  const int per = C / 32;
+  float acc[MAXC_PER_LANE];
+  for (int i = 0; i < per; ++i) acc[i] = 0.f;
+  uint8_t mk = 0;
+  if (l < len) {
+    // warp works on the transposed+flipped map t (rows i = w index, cols j = H-1-h): Ht = W, Wt = H
+    const float* M = tm + ((int64_t)b * L + l) * 16;
+    const float a = M[0], bb = M[1], tx = M[3] * inv_disc;
+    const float c = M[4], d = M[5], ty = M[7] * inv_disc;
+    const float cx = (float)H * 0.5f, cy = (float)W * 0.5f;    // centre = (Wt/2, Ht/2)
+    const float t0 = cx - a * cx - bb * cy + tx;
+    const float t1 = cy - c * cx - d * cy + ty;
+    const float det = a * d - bb * c;
+    const float ia = d / det, ib = -bb / det, ic = -c / det, id = a / det;
+    const float xd = (float)(H - 1 - h), yd = (float)w;        // destination pixel in t-space
+    const float sx = ia * (xd - t0) + ib * (yd - t1);
+    const float sy = ic * (xd - t0) + id * (yd - t1);
+    const uint16_t* src = x + (start + l) * (int64_t)H * W * C;
+    const float x0 = floorf(sx), y0 = floorf(sy);
+    const float fx = sx - x0, fy = sy - y0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int jx = (int)x0 + (t & 1), iy = (int)y0 + (t >> 1);   // t-space col / row
+      const float wgt = ((t & 1) ? fx : 1.f - fx) * ((t >> 1) ? fy : 1.f - fy);
+      if (jx < 0 || jx >= H || iy < 0 || iy >= W) continue;
+      // t[i = iy][j = jx] = x[h = H-1-jx][w = iy]
+      float v[MAXC_PER_LANE];
+      load_row(src + ((int64_t)(H - 1 - jx) * W + iy) * C, C, lane, bf16, v);
+      for (int i = 0; i < per; ++i) acc[i] = fmaf(v[i], wgt, acc[i]);
+    }
+    if (use_roi) {
+      // the ROI mask is warped on the un-transposed (H, W) canvas (torch_transformation_utils.py:43):
+      // centre (W/2, H/2), destination pixel (x = w, y = h)
+      const float rcx = (float)W * 0.5f, rcy = (float)H * 0.5f;
+      const float r0 = rcx - a * rcx - bb * rcy + tx;
+      const float r1 = rcy - c * rcx - d * rcy + ty;
+      const float mx = ia * ((float)w - r0) + ib * ((float)h - r1);
+      const float my = ic * ((float)w - r0) + id * ((float)h - r1);
+      const float rx = rintf(mx), ry = rintf(my);
+      mk = (rx >= 0.f && rx < (float)W && ry >= 0.f && ry < (float)H) ? 1 : 0;
+    } else {
+      mk = 1;
+    }
+  }
+  store_row(out + cell * C, C, lane, bf16, acc);
+  if (lane == 0) mask[(((int64_t)b * H + h) * W + w) * L + l] = mk;
+}
+
+// ------------------------------------------------------------------ layout converters (API boundary)
+// dtype codes: 0 f16, 1 bf16, 2 f32
+__device__ __forceinline__ float ld_any(const void* p, int64_t i, int dt) {
+  if (dt == 2) return reinterpret_cast<const float*>(p)[i];
+  return up1(reinterpret_cast<const uint16_t*>(p)[i], dt);
+}
+__device__ __forceinline__ void st_any(void* p, int64_t i, int dt, float v) {
+  if (dt == 2) reinterpret_cast<float*>(p)[i] = v;
+  else reinterpret_cast<uint16_t*>(p)[i] = pk1(v, dt);
+}
+// src NCHW (C channels) -> dst NHWC with Cpad channels (zero filled), or the reverse
+__global__ void permute_kernel(const void* __restrict__ src, void* __restrict__ dst, int N, int C, int H, int W,
+                               int Cpad, int to_nhwc, int sdt, int ddt) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (to_nhwc) {
+    const int64_t total = (int64_t)N * H * W * Cpad;
+    if (idx >= total) return;
+    const int c = (int)(idx % Cpad);
+    const int64_t pix = idx / Cpad;
+    const int64_t hw = (int64_t)H * W;
+    const int n = (int)(pix / hw);
+    const int64_t r = pix % hw;
+    st_any(dst, idx, ddt, c < C ? ld_any(src, ((int64_t)n * C + c) * hw + r, sdt) : 0.f);
+  } else {
+    const int64_t total = (int64_t)N * C * H * W;
+    if (idx >= total) return;
+    const int64_t hw = (int64_t)H * W;
+    const int64_t r = idx % hw;
+    const int c = (int)((idx / hw) % C);
+    const int n = (int)(idx / (hw * C));
+    st_any(dst, idx, ddt, ld_any(src, ((int64_t)n * hw + r) * Cpad + c, sdt));
+  }
+}
+
+inline unsigned blocks_for(int64_t threads, int bs) { return (unsigned)((threads + bs - 1) / bs); }
+inline bool ok_c(int C) { return C == 64 || C == 128 || C == 256; }
+
+}  // namespace
+
+using cobevt::fail;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t dtype, void* stream) {
+  if (!x || !y || npix <= 0) return fail(COBEVT_ERR_SHAPE, "pack_rgb8: bad args");
+  pack_rgb8_kernel<<<blocks_for(npix, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, npix, dtype);
+  return cobevt::check_launch("pack_rgb8");
+}
+
+extern "C" int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                                         int32_t dtype, void* stream) {
+  if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "maxpool: bad args");
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)N * OH * OW * (C / 8);
+  maxpool_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW, dtype);
+  return cobevt::check_launch("maxpool");
+}
+
+extern "C" int cobevt_bn_relu2(const void* x, const float* sa, const float* ba, void* ya, const float* sb,
+                                const float* bb, void* yb, int64_t rows, int32_t C, int32_t dtype, void* stream) {
+  if (!x || !sa || !ba || !ya || C % 8 || (yb && (!sb || !bb))) return fail(COBEVT_ERR_SHAPE, "bn_relu2: bad args");
+  bn_relu2_kernel<<<blocks_for(rows * (C / 8), 256), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
+                                                                         (uint16_t*)yb, rows, C, dtype);
+  return cobevt::check_launch("bn_relu2");
+}
+
+extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const float* w_img, const float* w_cam, void* out,
+                                 int32_t NV, int32_t h, int32_t w, float image_h, float image_w, int32_t C,
+                                 int32_t invert_intrinsic, int32_t dtype, void* stream) {
+  if (!I_inv || !E_inv || !w_img || !w_cam || !out || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "ray_embed: bad args (C must be 64/128/256)");
+  const int64_t threads = (int64_t)NV * h * w * 32;
+  ray_embed_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w,
+                                                                     image_h, image_w, C, invert_intrinsic, dtype);
+  return cobevt::check_launch("ray_embed");
+}
+
+extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* world, const float* w_bev, const float* b_bev,
+                                 const float* w_cam, const float* E_inv, void* out, int32_t BL, int32_t n, int32_t P,
+                                 int32_t C, float eps, int32_t dtype, void* stream) {
+  if (!x || !world || !w_bev || !b_bev || !w_cam || !E_inv || !out || !ok_c(C) || x_rows <= 0)
+    return fail(COBEVT_ERR_SHAPE, "bev_query: bad args");
+  const int64_t threads = (int64_t)BL * n * P * 32;
+  bev_query_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam,
+                                                                     E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  return cobevt::check_launch("bev_query");
+}
+
+extern "C" int cobevt_layernorm_rows(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                                      int32_t C, float eps, int32_t dtype, void* stream) {
+  if (!x || !y || !ok_c(C) || ((gamma == nullptr) != (beta == nullptr))) return fail(COBEVT_ERR_SHAPE, "layernorm: bad args");
+  layernorm_kernel<<<blocks_for(rows * 32, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, gamma, beta, (uint16_t*)y, rows, C, eps, dtype);
+  return cobevt::check_launch("layernorm");
+}
+
+extern "C" int cobevt_mean_views_ln(const void* x, void* y, int32_t B, int32_t L, int32_t P, int32_t C, float eps,
+                                     int32_t dtype, void* stream) {
+  if (!x || !y || !ok_c(C) || L <= 0) return fail(COBEVT_ERR_SHAPE, "mean_views_ln: bad args");
+  mean_views_ln_kernel<<<blocks_for((int64_t)B * P * 32, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, B, L, P, C, eps, dtype);
+  return cobevt::check_launch("mean_views_ln");
+}
+
+extern "C" int cobevt_sttf_regroup(const void* x, const float* tm, const int64_t* record_len, void* out, uint8_t* mask,
+                                    int32_t B, int32_t L, int32_t H, int32_t W, int32_t C, float discrete_ratio,
+                                    float downsample_rate, int32_t use_roi_mask, int32_t dtype, void* stream) {
+  if (!x || !tm || !record_len || !out || !mask || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "sttf: bad args");
+  const float inv_disc = 1.0f / (discrete_ratio * downsample_rate);
+  const int64_t threads = (int64_t)B * L * H * W * 32;
+  sttf_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, tm, record_len, (uint16_t*)out, mask, B, L, H,
+                                                                W, C, inv_disc, use_roi_mask, dtype);
+  return cobevt::check_launch("sttf");
+}
+
+extern "C" int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cpad,
+                               int32_t to_nhwc, int32_t src_dtype, int32_t dst_dtype, void* stream) {
+  if (!src || !dst || Cpad < C) return fail(COBEVT_ERR_SHAPE, "permute: bad args");
+  const int64_t total = to_nhwc ? (int64_t)N * H * W * Cpad : (int64_t)N * C * H * W;
+  permute_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src, dst, N, C, H, W, Cpad, to_nhwc, src_dtype, dst_dtype);
+  return cobevt::check_launch("permute");
+}

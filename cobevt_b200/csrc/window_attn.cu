@@ -93,7 +93,6 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
   const int head = item % p.heads;     item /= p.heads;
   const int win = item % a.n_win;
   const int b = item / a.n_win;
-  const int C = a.C;
   const int bf16 = p.dtype;
 
   if (tid == 0) {
@@ -137,7 +136,7 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
     if (key < a.Lk) {
       const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, key);
       if (t.in_range) {
-        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * C + head * DH;
+        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kv_stride + head * DH;
         srcK = kb_ + off * 2;
         srcV = vb_ + off * 2;
         nb = 16;
@@ -163,7 +162,7 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
       if (row_ok) {
         const int t_idx = p.q_mean ? pass * rows_per_pass + qrow : qrow;
         const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, t_idx);
-        const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
+        const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
         src = qb + off * 2;
         nb = 16;
       }
@@ -306,8 +305,8 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
   if (row_ok) {
     const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
     int64_t off;
-    if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
-    else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * C + head * DH;
+    if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+    else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
     uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
 #pragma unroll
     for (int ch = 0; ch < 4; ++ch) {
@@ -349,6 +348,11 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   const int rows = p->q_mean ? qm.w1 * qm.w2 : a.Lq;
   a.q_tiles = cobevt::ceil_div(rows, TILE_Q);
   a.C = p->heads * DH;
+  if (a.p.q_stride == 0) a.p.q_stride = a.C;
+  if (a.p.kv_stride == 0) a.p.kv_stride = a.C;
+  if (a.p.out_stride == 0) a.p.out_stride = a.C;
+  if (a.p.q_stride < a.C || a.p.kv_stride < a.C || a.p.out_stride < a.C || (a.p.q_stride | a.p.kv_stride | a.p.out_stride) % 8)
+    return cobevt::fail(COBEVT_ERR_SHAPE, "attn: token strides must be >= heads*32 and multiples of 8");
   if (p->bias && p->q_mean) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias with q_mean");
   if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: dtype");
   const bool bf = p->dtype == COBEVT_BF16;

@@ -1,0 +1,375 @@
+"""Inference engine of the FAX hot path: weight plans (folded + packed once) and the kernel
+sequences that run them.  Everything between the model's input and output tensors stays
+NHWC 16-bit in HBM; every arithmetic step is a call into libcobevt_sm100.so (ops.py).
+
+Folding done at plan time (all exact re-associations of the reference math):
+  * eval BatchNorm after a conv          -> scaled weights + bias
+  * LayerNorm affine in front of a Linear -> W diag(gamma), W beta + b   (kernels then only
+    ever need the un-affined normalised row, produced by the preceding epilogue)
+  * PixelUnshuffle(2) between two convs   -> a 6x3 stride-(2,1) conv over the (H, W/2, 2C) view
+  * nearest x2 upsample before a conv     -> index shift in the implicit-GEMM gather
+  * attn2's `repeat(query, n)` + mean     -> one copy (survey quirk Q1)
+"""
+import torch
+
+from . import ops
+from .ops import PackedConv, ACT_NONE, ACT_RELU, ACT_GELU
+
+LN_EPS = 1e-5
+
+
+# --------------------------------------------------------------------------- folding helpers
+def _bn_scale_shift(bn):
+    s = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    return s, bn.bias.detach().float() - bn.running_mean.detach().float() * s
+
+
+def fold_conv_bn(conv, bn):
+    """conv (no act) followed by eval BatchNorm -> (weight, bias)."""
+    w = conv.weight.detach().float()
+    b = conv.bias.detach().float() if conv.bias is not None else torch.zeros(w.shape[0])
+    if bn is None:
+        return w, (b if conv.bias is not None else None)
+    s, t = _bn_scale_shift(bn)
+    s, t = s.to(w.device), t.to(w.device)
+    return w * s.view(-1, 1, 1, 1), b.to(w.device) * s + t
+
+
+def fold_ln_linear(ln, lin):
+    """Linear(LayerNorm(x)) = (W diag(g)) xhat + (W beta + b)."""
+    w = lin.weight.detach().float()
+    g, be = ln.weight.detach().float(), ln.bias.detach().float()
+    b = w @ be
+    if lin.bias is not None:
+        b = b + lin.bias.detach().float()
+    return w * g[None, :], b
+
+
+def _dev_f32(t, device):
+    return t.detach().float().contiguous().to(device)
+
+
+# --------------------------------------------------------------------------- ResNet trunk
+class ResNetPlan:
+    """BasicBlock / Bottleneck ResNet trunk up to the deepest picked level
+    (resnet_ms.py:46-89; levels past max(id_pick) cannot influence the output and are skipped)."""
+
+    def __init__(self, trunk, device, dtype, n_levels):
+        self.dtype = dtype
+        w, b = fold_conv_bn(trunk.conv1, trunk.bn1)
+        self.stem = PackedConv(w, b, device, dtype, cin_pad=8)
+        self.levels = []
+        for li in range(n_levels):
+            blocks = []
+            for blk in getattr(trunk, f"layer{li + 1}"):
+                convs = []
+                names = [("conv1", "bn1"), ("conv2", "bn2")] + ([("conv3", "bn3")] if hasattr(blk, "conv3") else [])
+                for cn, bnn in names:
+                    conv = getattr(blk, cn)
+                    w, b = fold_conv_bn(conv, getattr(blk, bnn))
+                    convs.append((PackedConv(w, b, device, dtype), conv.stride[0], conv.padding[0]))
+                ds = None
+                if blk.downsample is not None:
+                    w, b = fold_conv_bn(blk.downsample[0], blk.downsample[1])
+                    ds = (PackedConv(w, b, device, dtype), blk.downsample[0].stride[0])
+                blocks.append((convs, ds))
+            self.levels.append(blocks)
+
+    def run(self, images):
+        """images (NI, H, W, 3) fp32 -> list of NHWC 16-bit feature maps, one per level."""
+        x = ops.pack_rgb8(images, self.dtype)
+        x, _, _ = ops.conv2d_nhwc(x, self.stem, stride=2, pad=3, act=ACT_RELU)
+        x = ops.maxpool3x3s2(x)
+        feats = []
+        for blocks in self.levels:
+            for convs, ds in blocks:
+                idt = x
+                if ds is not None:
+                    idt, _, _ = ops.conv2d_nhwc(x, ds[0], stride=ds[1], pad=0)
+                y = x
+                for ci, (pc, st, pd) in enumerate(convs):
+                    last = ci == len(convs) - 1
+                    y, _, _ = ops.conv2d_nhwc(y, pc, stride=st, pad=pd, act=ACT_RELU, res=idt if last else None)
+                x = y
+            feats.append(x)
+        return feats
+
+
+class BottleneckPlan:
+    """torchvision Bottleneck(c, c//4) with eval BN folded (fax_modules.py:10,472)."""
+
+    def __init__(self, blk, device, dtype):
+        self.c = [PackedConv(*fold_conv_bn(getattr(blk, f"conv{i}"), getattr(blk, f"bn{i}")), device, dtype) for i in (1, 2, 3)]
+
+    def run(self, x):
+        y, _, _ = ops.conv2d_nhwc(x, self.c[0], act=ACT_RELU)
+        y, _, _ = ops.conv2d_nhwc(y, self.c[1], pad=1, act=ACT_RELU)
+        y, _, _ = ops.conv2d_nhwc(y, self.c[2], act=ACT_RELU, res=x)
+        return y
+
+
+class DownsamplePlan:
+    """conv3x3 -> PixelUnshuffle(2) -> conv3x3-BN-ReLU -> conv1x1-BN (fax_modules.py:476-489)."""
+
+    def __init__(self, seq, device, dtype):
+        conv_a, _, conv_b, bn_b, _, conv_c, bn_c = list(seq)
+        self.a = PackedConv(conv_a.weight.detach().float(), None, device, dtype)
+        cq = conv_a.weight.shape[0]                      # channels before the unshuffle
+        wb, bb = fold_conv_bn(conv_b, bn_b)              # (Co, cq*4, 3, 3), in-channel = c*4 + dy*2 + dx
+        co = wb.shape[0]
+        wb = wb.reshape(co, cq, 2, 2, 3, 3)              # co c dy dx ky kx
+        wb = wb.permute(0, 3, 1, 4, 2, 5)                # co dx c ky dy kx
+        wb = wb.reshape(co, 2 * cq, 6, 3)                # in-channel = dx*cq + c ; kh = 2*ky + dy
+        self.b = PackedConv(wb, bb, device, dtype)
+        self.c = PackedConv(*fold_conv_bn(conv_c, bn_c), device, dtype)
+        self.cq = cq
+
+    def run(self, x, want_ln):
+        N, H, W, _ = x.shape
+        y, _, _ = ops.conv2d_nhwc(x, self.a, pad=1)                       # (N, H, W, cq)
+        y = y.view(N, H, W // 2, 2 * self.cq)                            # merge dx into channels
+        y, _, _ = ops.conv2d_nhwc(y, self.b, stride=(2, 1), pad=(2, 1), act=ACT_RELU)
+        return ops.conv2d_nhwc(y, self.c, ln_out=want_ln)                # x, None, LN0(x)
+
+
+# --------------------------------------------------------------------------- FAX stage
+class CrossAttnPlan:
+    """CrossWinAttention weights: LayerNorm affines folded into q/k/v projections."""
+
+    def __init__(self, m, device, dtype):
+        self.q = PackedConv(*fold_ln_linear(m.to_q[0], m.to_q[1]), device, dtype)
+        wk, bk = fold_ln_linear(m.to_k[0], m.to_k[1])
+        wv, bv = fold_ln_linear(m.to_v[0], m.to_v[1])
+        self.k = PackedConv(wk, bk, device, dtype)
+        self.v = PackedConv(wv, bv, device, dtype)
+        # a zero-padded key/value row becomes Linear(LayerNorm(0)) = W beta + b (quirk Q2)
+        self.k_pad = bk.to(dtype).to(device)
+        self.v_pad = bv.to(dtype).to(device)
+        self.proj = PackedConv(m.proj.weight.detach().float(), m.proj.bias.detach().float(), device, dtype)
+        self.heads, self.dim_head = m.heads, m.dim_head
+        self.scale = m.scale
+
+
+class FaxStagePlan:
+    def __init__(self, cva, world, device, dtype):
+        self.dtype = dtype
+        self.dim = cva.prenorm_1.weight.shape[0]
+        self.q_win, self.feat_win = tuple(cva.q_win_size), tuple(cva.feat_win_size)
+        self.bev_flag, self.skip = cva.bev_embed_flag, cva.skip
+        self.image_h, self.image_w = cva.image_height, cva.image_width
+        self.no_img_feat = cva.feature_proj is None
+        sl, tl = _bn_scale_shift(cva.feature_linear[0])
+        self.bn_l = (_dev_f32(sl, device), _dev_f32(tl, device))
+        self.f_lin = PackedConv(cva.feature_linear[2].weight.detach().float(), None, device, dtype)
+        if not self.no_img_feat:
+            sp, tp = _bn_scale_shift(cva.feature_proj[0])
+            self.bn_p = (_dev_f32(sp, device), _dev_f32(tp, device))
+            self.f_proj = PackedConv(cva.feature_proj[2].weight.detach().float(), None, device, dtype)
+        self.w_img = _dev_f32(cva.img_embed.weight.reshape(self.dim, 4), device)
+        self.w_cam = _dev_f32(cva.cam_embed.weight.reshape(self.dim, 4), device)
+        if self.bev_flag:
+            self.w_bev = _dev_f32(cva.bev_embed.weight.reshape(self.dim, 2), device)
+            self.b_bev = _dev_f32(cva.bev_embed.bias, device)
+            self.world = _dev_f32(world.reshape(2, -1), device)
+        self.a1 = CrossAttnPlan(cva.cross_win_attend_1, device, dtype)
+        self.a2 = CrossAttnPlan(cva.cross_win_attend_2, device, dtype)
+        self.m1a = PackedConv(*fold_ln_linear(cva.prenorm_1, cva.mlp_1[0]), device, dtype)
+        self.m1b = PackedConv(cva.mlp_1[2].weight.detach().float(), cva.mlp_1[2].bias.detach().float(), device, dtype)
+        self.m2a = PackedConv(*fold_ln_linear(cva.prenorm_2, cva.mlp_2[0]), device, dtype)
+        self.m2b = PackedConv(cva.mlp_2[2].weight.detach().float(), cva.mlp_2[2].bias.detach().float(), device, dtype)
+        self.post_g = _dev_f32(cva.postnorm.weight, device)
+        self.post_b = _dev_f32(cva.postnorm.bias, device)
+
+    def run(self, x, x_ln, x_rows, feat, n, intrinsic, E_inv, invert_intrinsic=True):
+        """x: (rows, H, W, d) residual stream (rows == BL, or 1 for the broadcast prior);
+        x_ln: LayerNorm0(x) or None; feat: (BL*n, h, w, Cf).  Returns (BL, H, W, d)."""
+        d = self.dim
+        BLn, h, w, _ = feat.shape
+        BL = BLn // n
+        H, W = x.shape[1:3]
+        P = H * W
+        # ---- key / value token maps (fax_modules.py:343-358,377-384) -------------------------
+        if self.no_img_feat:
+            fb, _ = ops.bn_relu2(feat, *self.bn_l)
+        else:
+            fa, fb = ops.bn_relu2(feat, *self.bn_p, *self.bn_l)
+        img = ops.ray_embed(intrinsic, E_inv, self.w_img, self.w_cam, h, w, self.image_h, self.image_w, d,
+                            self.dtype, invert_intrinsic=invert_intrinsic)
+        if self.no_img_feat:
+            k_hat = ops.layernorm_rows(img)
+        else:
+            _, _, k_hat = ops.conv2d_nhwc(fa, self.f_proj, res=img, want16=False, ln_out=True)
+        _, _, v_hat = ops.conv2d_nhwc(fb, self.f_lin, want16=False, ln_out=True)
+        kv = lambda pc, t: ops.conv2d_nhwc(t, pc)[0].view(BL, n, h, w, d)
+        k1, v1 = kv(self.a1.k, k_hat), kv(self.a1.v, v_hat)
+        k2, v2 = kv(self.a2.k, k_hat), kv(self.a2.v, v_hat)
+        fh, fw = self.feat_win
+        hp = h if h % fh == 0 else ((h + fh) // fh) * fh                   # pad_divisble, :315-321
+        wp = w if w % fw == 0 else ((w + fw) // fw) * fw
+        padded = (hp, wp) != (h, w)
+        # ---- queries ---------------------------------------------------------------------------
+        if self.bev_flag:
+            q_hat = ops.bev_query(x.reshape(-1, d), self.world, self.w_bev, self.b_bev, self.w_cam, E_inv, BL, n, P)
+            nq = n
+        else:
+            q_hat = x_ln if x_ln is not None else ops.layernorm_rows(x)
+            nq = 1
+        q1 = ops.linear_tokens(q_hat.reshape(-1, d), self.a1.q)[0].view(BL, nq, H, W, d)
+        qm = ops.token_map(nq, H, W, *self.q_win, False)
+        km = ops.token_map(n, hp, wp, fh, fw, False, Hv=h, Wv=w)
+        a = ops.window_attention(q1, k1, v1, qm, km, self.a1.heads, self.a1.scale, True,
+                                 k_pad=self.a1.k_pad if padded else None, v_pad=self.a1.v_pad if padded else None)
+        skip = x.reshape(-1, d) if self.skip else None
+        rr = P * x_rows if (self.skip and x_rows != BL) else 0
+        z, _, z_ln = ops.linear_tokens(a.reshape(-1, d), self.a1.proj, res=skip, res_rows=rr, ln_out=True)
+        hmid = ops.linear_tokens(z_ln, self.m1a, act=ACT_GELU)[0]
+        z, _, z_ln = ops.linear_tokens(hmid, self.m1b, res=z, ln_out=True)
+        # ---- local window <-> dilated grid (fax_modules.py:413-433) ---------------------------
+        q2 = ops.linear_tokens(z_ln, self.a2.q)[0].view(BL, 1, H, W, d)
+        qm = ops.token_map(1, H, W, *self.q_win, False)
+        km = ops.token_map(n, hp, wp, fh, fw, True, Hv=h, Wv=w)
+        a = ops.window_attention(q2, k2, v2, qm, km, self.a2.heads, self.a2.scale, True,
+                                 k_pad=self.a2.k_pad if padded else None, v_pad=self.a2.v_pad if padded else None)
+        z2, _, z_ln = ops.linear_tokens(a.reshape(-1, d), self.a2.proj, res=z if self.skip else None, ln_out=True)
+        hmid = ops.linear_tokens(z_ln, self.m2a, act=ACT_GELU)[0]
+        _, _, out = ops.linear_tokens(hmid, self.m2b, res=z2, want16=False, ln_out=True,
+                                      ln_gamma=self.post_g, ln_beta=self.post_b)
+        return out.view(BL, H, W, d)
+
+
+class GlobalAttnPlan:
+    """fax_modules.Attention (:93-176): 1024-token self-attention with 2-D rel-pos bias."""
+
+    def __init__(self, m, device, dtype):
+        self.qkv = PackedConv(m.to_qkv.weight.detach().float(), None, device, dtype)
+        self.out = PackedConv(m.to_out[0].weight.detach().float(), None, device, dtype)
+        self.heads, self.scale = m.heads, m.scale
+        bias = m.rel_pos_bias.weight.detach().float()[m.rel_pos_indices.to(m.rel_pos_bias.weight.device)]  # T T h
+        self.bias = bias.permute(2, 0, 1).contiguous().to(device)
+
+    def run(self, x):
+        BL, H, W, d = x.shape
+        qkv = ops.linear_tokens(x, self.qkv)[0].view(BL, 1, H, W, 3 * d)
+        m = ops.token_map(1, H, W, H, W, False)
+        a = ops.window_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], m, m, self.heads, self.scale,
+                                 False, bias=self.bias)
+        return ops.linear_tokens(a.view(BL, H, W, d), self.out)[0]
+
+
+class FaxPlan:
+    def __init__(self, fax, device, dtype):
+        self.dtype = dtype
+        be = fax.bev_embedding
+        self.stages = [FaxStagePlan(cv, getattr(be, f"grid{i}")[:2], device, dtype)
+                       for i, cv in enumerate(fax.cross_views)]
+        self.layers = [[BottleneckPlan(b, device, dtype) for b in seq] for seq in fax.layers]
+        self.down = [DownsamplePlan(seq[0], device, dtype) for seq in fax.downsample_layers]
+        self.self_attn = GlobalAttnPlan(fax.self_attn, device, dtype) if fax.self_attn is not None else None
+        prior = be.learned_features.detach().float().permute(1, 2, 0).contiguous()         # H W d
+        self.prior = prior.to(dtype).to(device)[None]
+
+    def run(self, feats, n, intrinsic, E_inv, invert_intrinsic=True):
+        """feats: list of (BL*n, h, w, Cf) NHWC; intrinsic (BL*n,3,3), E_inv (BL*n,4,4) fp32."""
+        BL = feats[0].shape[0] // n
+        x, x_ln, x_rows = self.prior, None, 1
+        for i, st in enumerate(self.stages):
+            x = st.run(x, x_ln, x_rows, feats[i], n, intrinsic, E_inv, invert_intrinsic)
+            x_rows = BL
+            for b in self.layers[i]:
+                x = b.run(x)
+            x_ln = None
+            if i < len(self.stages) - 1:
+                nxt_needs_ln = not self.stages[i + 1].bev_flag
+                x, _, x_ln = self.down[i].run(x, nxt_needs_ln)
+        if self.self_attn is not None:
+            x = self.self_attn.run(x)
+        return x
+
+
+# --------------------------------------------------------------------------- FuseBEVT
+class SwapAttnPlan:
+    def __init__(self, prenorm_attn, prenorm_ffd, device, dtype):
+        at = prenorm_attn.fn
+        self.qkv = PackedConv(*fold_ln_linear(prenorm_attn.norm, at.to_qkv), device, dtype)
+        self.out = PackedConv(at.to_out[0].weight.detach().float(), None, device, dtype)
+        tbl = at.relative_position_bias_table.weight.detach().float()
+        idx = at.relative_position_index.to(tbl.device)
+        self.bias = tbl[idx].permute(2, 0, 1).contiguous().to(device)      # heads T T
+        self.heads, self.scale = at.heads, at.scale
+        ff = prenorm_ffd.fn.net
+        self.f1 = PackedConv(*fold_ln_linear(prenorm_ffd.norm, ff[0]), device, dtype)
+        self.f2 = PackedConv(ff[3].weight.detach().float(), ff[3].bias.detach().float(), device, dtype)
+
+
+class FusionPlan:
+    """SwapFusionEncoder (swap_fusion_modules.py:233-286)."""
+
+    def __init__(self, enc, device, dtype):
+        self.use_mask = enc.mask
+        self.ws = enc.window_size
+        self.blocks = []
+        for blk in enc.layers:
+            if enc.mask:
+                pairs = [(blk.window_attention, blk.window_ffd), (blk.grid_attention, blk.grid_ffd)]
+            else:
+                pairs = [(blk.block[1], blk.block[2]), (blk.block[5], blk.block[6])]
+            self.blocks.append([SwapAttnPlan(a, f, device, dtype) for a, f in pairs])
+        self.head = PackedConv(*fold_ln_linear(enc.mlp_head[2], enc.mlp_head[3]), device, dtype)
+
+    def run(self, x, mask):
+        """x (B, L, H, W, d) 16-bit; mask (B, H, W, L) uint8 or None -> (B, H, W, d)."""
+        B, L, H, W, d = x.shape
+        x = x.reshape(-1, d)
+        x_ln = ops.layernorm_rows(x)
+        for blk in self.blocks:
+            for kind, sp in enumerate(blk):
+                qkv = ops.linear_tokens(x_ln, sp.qkv)[0].view(B, L, H, W, 3 * d)
+                m = ops.token_map(L, H, W, self.ws, self.ws, kind == 1)
+                a = ops.window_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], m, m, sp.heads, sp.scale,
+                                         False, bias=sp.bias, key_mask=mask if self.use_mask else None)
+                x, _, x_ln = ops.linear_tokens(a.reshape(-1, d), sp.out, res=x, ln_out=True)
+                hmid = ops.linear_tokens(x_ln, sp.f1, act=ACT_GELU)[0]
+                x, _, x_ln = ops.linear_tokens(hmid, sp.f2, res=x, ln_out=True)
+        m_ln = ops.mean_views_ln(x.view(B, L, H * W, d))
+        return ops.linear_tokens(m_ln, self.head)[0].view(B, H, W, d)
+
+
+# --------------------------------------------------------------------------- decoder / head
+class DecoderPlan:
+    """NaiveDecoder (naive_decoder.py:62-91): per level conv-BN-ReLU, nearest x2, conv-BN-ReLU."""
+
+    def __init__(self, dec, device, dtype):
+        mods = list(dec.decoder)
+        self.levels = []
+        for j in range(len(mods) // 6):
+            a = PackedConv(*fold_conv_bn(mods[6 * j], mods[6 * j + 1]), device, dtype)
+            b = PackedConv(*fold_conv_bn(mods[6 * j + 3], mods[6 * j + 4]), device, dtype)
+            self.levels.append((a, b))
+
+    def run(self, x):
+        for a, b in self.levels:
+            x, _, _ = ops.conv2d_nhwc(x, a, pad=1, act=ACT_RELU)
+            x, _, _ = ops.conv2d_nhwc(x, b, pad=1, act=ACT_RELU, in_upsample=True)
+        return x
+
+
+class SegHeadPlan:
+    def __init__(self, head, device, dtype):
+        self.target = head.target
+        mk = lambda c: PackedConv(c.weight.detach().float(), c.bias.detach().float(), device, dtype)
+        self.dyn = mk(head.dynamic_head) if head.target in ("dynamic", "both") else None
+        self.sta = mk(head.static_head) if head.target in ("static", "both") else None
+
+    def run(self, x, b, l):
+        """x (b*l, H, W, C) -> dict of (b, l, classes, H, W) fp32 (bev_seg_head.py:35-61)."""
+        out = {}
+        for key, pc in (("dynamic_seg", self.dyn), ("static_seg", self.sta)):
+            if pc is not None:
+                _, y32, _ = ops.conv2d_nhwc(x, pc, pad=1, want16=False, out32=True)
+                y = ops.nhwc_to_nchw(y32, torch.float32)
+                out[key] = y.view(b, l, *y.shape[1:])
+        if "dynamic_seg" not in out:
+            out["dynamic_seg"] = torch.zeros_like(out["static_seg"])
+        if "static_seg" not in out:
+            out["static_seg"] = torch.zeros_like(out["dynamic_seg"])
+        return out

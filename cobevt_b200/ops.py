@@ -75,29 +75,39 @@ class PackedConv:
         self.bias = None if bias is None else bias.detach().float().contiguous().to(device)
 
 
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
 def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=None,
-                out32=False, want16=True, ln_out=False, in_upsample=False, ln_eps=1e-5):
+                out32=False, want16=True, ln_out=False, ln_gamma=None, ln_beta=None,
+                in_upsample=False, ln_eps=1e-5, res_rows=0):
     """x: (N, H, W, Cin) 16-bit contiguous.  Returns (y16 | None, y32 | None, y_ln | None)."""
     assert x.is_cuda and x.is_contiguous() and x.dim() == 4
     N, H, W, Cin = x.shape
     assert Cin == pc.cin, f"Cin {Cin} != packed {pc.cin}"
     Hl, Wl = (2 * H, 2 * W) if in_upsample else (H, W)
-    OH = (Hl + 2 * pad - pc.kh) // stride + 1
-    OW = (Wl + 2 * pad - pc.kw) // stride + 1
+    (sh, sw), (ph, pw) = _pair(stride), _pair(pad)
+    OH = (Hl + 2 * ph - pc.kh) // sh + 1
+    OW = (Wl + 2 * pw - pc.kw) // sw + 1
     M = N * OH * OW
     y = out if out is not None else (torch.empty((N, OH, OW, pc.cout), dtype=x.dtype, device=x.device) if want16 else None)
     y32 = torch.empty((N, OH, OW, pc.cout), dtype=torch.float32, device=x.device) if out32 else None
     yln = torch.empty((N, OH, OW, pc.cout), dtype=x.dtype, device=x.device) if ln_out else None
+    rrows = res_rows if res_rows else M
     if res is not None:
-        assert res.is_contiguous() and res.numel() == M * pc.cout and res.dtype == x.dtype
+        assert res.is_contiguous() and res.numel() == rrows * pc.cout and res.dtype == x.dtype
     if res32 is not None:
-        assert res32.is_contiguous() and res32.numel() == M * pc.cout and res32.dtype == torch.float32
+        assert res32.is_contiguous() and res32.numel() == rrows * pc.cout and res32.dtype == torch.float32
     p = ConvParams()
     p.x, p.w, p.bias = _ptr(x), _ptr(pc.w), _ptr(pc.bias)
     p.res, p.res32, p.y, p.y32, p.y_ln = _ptr(res), _ptr(res32), _ptr(y), _ptr(y32), _ptr(yln)
     p.N, p.Hin, p.Win, p.Cin = N, H, W, Cin
     p.OH, p.OW, p.Cout = OH, OW, pc.cout
-    p.KH, p.KW, p.stride, p.pad = pc.kh, pc.kw, stride, pad
+    p.KH, p.KW = pc.kh, pc.kw
+    p.stride_h, p.stride_w, p.pad_h, p.pad_w = sh, sw, ph, pw
+    p.res_rows = res_rows
+    p.ln_gamma, p.ln_beta = _ptr(ln_gamma), _ptr(ln_beta)
     p.in_upsample = 1 if in_upsample else 0
     p.act, p.dtype, p.block_n, p.ln_eps = act, dtype_code(x.dtype), pc.block_n, ln_eps
     _lib.check(_lib.lib().cobevt_conv2d_nhwc_fwd(ctypes.byref(p), _stream()), "cobevt_conv2d_nhwc_fwd")
@@ -130,9 +140,21 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
 
     Returns (B, Hq, Wq, C) if q_mean else (B, qviews, Hq, Wq, C).
     """
-    assert q.is_cuda and q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
-    B, qv, Hq, Wq, C = q.shape
-    assert C == heads * 32 and k.shape == v.shape and k.shape[-1] == C
+    C = heads * 32
+    B, qv, Hq, Wq, _ = q.shape
+
+    def tok_stride(t):
+        # t may be a last-dim slice of a wider contiguous token tensor
+        assert t.is_cuda and t.shape[-1] == C and t.stride(-1) == 1
+        ts = t.stride(-2)
+        exp = ts
+        for d in range(t.dim() - 2, -1, -1):
+            assert t.stride(d) == exp or t.shape[d] == 1, "tokens must be densely strided"
+            exp *= t.shape[d]
+        return ts
+
+    qs, ks, vs = tok_stride(q), tok_stride(k), tok_stride(v)
+    assert ks == vs and k.shape == v.shape
     assert (qv, Hq, Wq) == (qmap.views, qmap.Hv, qmap.Wv)
     assert tuple(k.shape[1:4]) == (kvmap.views, kvmap.Hv, kvmap.Wv)
     out = torch.empty((B, Hq, Wq, C) if q_mean else (B, qv, Hq, Wq, C), dtype=q.dtype, device=q.device)
@@ -146,5 +168,118 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p.bias, p.key_mask = _ptr(bias), _ptr(key_mask)
     p.qmap, p.kvmap = qmap, kvmap
     p.B, p.heads, p.q_mean, p.scale, p.dtype = B, heads, 1 if q_mean else 0, scale, dtype_code(q.dtype)
+    p.q_stride, p.kv_stride, p.out_stride = qs, ks, C
     _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
     return out
+
+
+# --------------------------------------------------------------------------- element-wise ops
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def pack_rgb8(x, dtype):
+    """x (..., 3) fp32 -> (..., 8) 16-bit (channels 3..7 zero)."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3
+    y = torch.empty(*x.shape[:-1], 8, dtype=dtype, device=x.device)
+    npix = x.numel() // 3
+    _lib.check(_lib.lib().cobevt_pack_rgb8(_ptr(x), _ptr(y), npix, dtype_code(dtype), _stream()), "cobevt_pack_rgb8")
+    return y
+
+
+def maxpool3x3s2(x):
+    N, H, W, C = x.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(N, OH, OW, C, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().cobevt_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), N, H, W, C, dtype_code(x.dtype), _stream()),
+               "cobevt_maxpool3x3s2_nhwc")
+    return y
+
+
+def bn_relu2(x, sa, ba, sb=None, bb=None):
+    C = x.shape[-1]
+    rows = x.numel() // C
+    ya = torch.empty_like(x)
+    yb = torch.empty_like(x) if sb is not None else None
+    _lib.check(_lib.lib().cobevt_bn_relu2(_ptr(x), _f32(sa), _f32(ba), _ptr(ya), _ptr(sb), _ptr(bb), _ptr(yb),
+                                          rows, C, dtype_code(x.dtype), _stream()), "cobevt_bn_relu2")
+    return ya, yb
+
+
+def ray_embed(I_inv, E_inv, w_img, w_cam, h, w, image_h, image_w, C, dtype, invert_intrinsic=False):
+    """I_inv: (NV,3,3) inverse intrinsics, or the intrinsics themselves with invert_intrinsic=True."""
+    NV = I_inv.shape[0]
+    out = torch.empty(NV, h, w, C, dtype=dtype, device=I_inv.device)
+    _lib.check(_lib.lib().cobevt_ray_embed(_f32(I_inv), _f32(E_inv), _f32(w_img), _f32(w_cam), _ptr(out), NV, h, w,
+                                           float(image_h), float(image_w), C, 1 if invert_intrinsic else 0,
+                                           dtype_code(dtype), _stream()),
+               "cobevt_ray_embed")
+    return out
+
+
+def bev_query(x, world, w_bev, b_bev, w_cam, E_inv, BL, n, P, eps=1e-5):
+    """x: (rows, C) 16-bit with rows == BL*P or rows == P (broadcast prior)."""
+    C = x.shape[-1]
+    x_rows = x.numel() // C
+    out = torch.empty(BL, n, P, C, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().cobevt_bev_query(_ptr(x), x_rows, _f32(world), _f32(w_bev), _f32(b_bev), _f32(w_cam),
+                                           _f32(E_inv), _ptr(out), BL, n, P, C, eps, dtype_code(x.dtype), _stream()),
+               "cobevt_bev_query")
+    return out
+
+
+def layernorm_rows(x, gamma=None, beta=None, eps=1e-5):
+    C = x.shape[-1]
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    _lib.check(_lib.lib().cobevt_layernorm_rows(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, eps,
+                                                dtype_code(x.dtype), _stream()), "cobevt_layernorm_rows")
+    return y
+
+
+def mean_views_ln(x, eps=1e-5):
+    """x (B, L, P, C) -> (B, P, C)."""
+    B, L, P, C = x.shape
+    y = torch.empty(B, P, C, dtype=x.dtype, device=x.device)
+    _lib.check(_lib.lib().cobevt_mean_views_ln(_ptr(x), _ptr(y), B, L, P, C, eps, dtype_code(x.dtype), _stream()),
+               "cobevt_mean_views_ln")
+    return y
+
+
+def sttf_regroup(x, tm, record_len, B, L, discrete_ratio, downsample_rate, use_roi_mask):
+    """x (sumL, H, W, C) 16-bit; tm (B, L, 4, 4) fp32; record_len (B,) int64 -- all on device."""
+    _, H, W, C = x.shape
+    assert tm.dtype == torch.float32 and tm.is_contiguous() and record_len.dtype == torch.int64
+    out = torch.empty(B, L, H, W, C, dtype=x.dtype, device=x.device)
+    mask = torch.empty(B, H, W, L, dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib().cobevt_sttf_regroup(_ptr(x), _ptr(tm), _ptr(record_len), _ptr(out), _ptr(mask), B, L, H, W, C,
+                                              float(discrete_ratio), float(downsample_rate), 1 if use_roi_mask else 0,
+                                              dtype_code(x.dtype), _stream()), "cobevt_sttf_regroup")
+    return out, mask
+
+
+def _any_code(dt):
+    return 2 if dt == torch.float32 else dtype_code(dt)
+
+
+def nchw_to_nhwc(x, dtype, cpad=None):
+    """(N, C, H, W) any float dtype -> (N, H, W, Cpad) `dtype`."""
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    cp = cpad or C
+    y = torch.empty(N, H, W, cp, dtype=dtype, device=x.device)
+    _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 1, _any_code(x.dtype), _any_code(dtype), _stream()),
+               "cobevt_permute")
+    return y
+
+
+def nhwc_to_nchw(x, dtype, c=None):
+    """(N, H, W, Cpad) -> (N, C, H, W) `dtype` (first C channels)."""
+    assert x.is_contiguous()
+    N, H, W, cp = x.shape
+    C = c or cp
+    y = torch.empty(N, C, H, W, dtype=dtype, device=x.device)
+    _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 0, _any_code(x.dtype), _any_code(dtype), _stream()),
+               "cobevt_permute")
+    return y

@@ -53,11 +53,16 @@ typedef struct {
   const float* res32;  /* (M, Cout) fp32 residual, or NULL                            */
   void* y;             /* (M, Cout) 16-bit output or NULL                             */
   float* y32;          /* (M, Cout) fp32 output or NULL                               */
-  void* y_ln;          /* (M, Cout) 16-bit LayerNorm-normalised copy (no affine) or NULL;
-                          requires Cout == block_n == 128                             */
+  void* y_ln;          /* (M, Cout) 16-bit LayerNorm of the output row, or NULL; requires
+                          Cout == block_n == 128                                      */
+  const float* ln_gamma; /* [Cout] affine of y_ln, or NULL for the plain normalised row
+                          (consumers fold their own LayerNorm affine into their weights) */
+  const float* ln_beta;
   int32_t N, Hin, Win, Cin; /* physical input extents                                  */
   int32_t OH, OW, Cout;     /* M = N*OH*OW                                             */
-  int32_t KH, KW, stride, pad;
+  int32_t KH, KW;
+  int32_t stride_h, stride_w, pad_h, pad_w;
+  int32_t res_rows;    /* >0: residual row index is (m % res_rows) (broadcast over batch)  */
   int32_t in_upsample; /* 1: logical input is the physical one nearest-upsampled x2    */
   int32_t act;         /* COBEVT_ACT_*                                                 */
   int32_t dtype;       /* COBEVT_F16 / COBEVT_BF16                                     */
@@ -91,7 +96,7 @@ typedef struct {
 } CobevtTokenMap;
 
 typedef struct {
-  const void* q;      /* (B, q.views, q.Hv, q.Wv, C) 16-bit, C = heads*32            */
+  const void* q;      /* (B, q.views, q.Hv, q.Wv, :) 16-bit, head h at channels [32h, 32h+32) */
   const void* k;      /* (B, kv.views, kv.Hv, kv.Wv, C)                              */
   const void* v;
   void* out;          /* q_mean ? (B, q.Hv, q.Wv, C) : (B, q.views, q.Hv, q.Wv, C)   */
@@ -101,6 +106,8 @@ typedef struct {
   const uint8_t* key_mask; /* (B, kv.Hv, kv.Wv, kv.views) 1 = keep, 0 = -inf; or NULL */
   CobevtTokenMap qmap, kvmap;
   int32_t B, heads;
+  int32_t q_stride, kv_stride, out_stride; /* token strides in elements (>= heads*32);
+                         lets q/k/v be column slices of one fused projection output    */
   int32_t q_mean;     /* 1: q views are separate passes averaged (CrossWinAttention
                          mean over n, fax_modules.py:243); 0: views are extra rows   */
   float scale;
@@ -108,6 +115,49 @@ typedef struct {
 } CobevtAttnParams;
 
 int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * HBM-bound element-wise / gather kernels (dtype: 0 f16, 1 bf16; permute also 2 = f32)
+ * -------------------------------------------------------------------------*/
+/* (npix,3) fp32 RGB -> (npix,8) 16-bit, channels 3..7 zero.  Replaces the
+ * .permute(0,3,1,2).contiguous() copy of resnet_ms.py:62-65 (the stem reads NHWC8). */
+int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t dtype, void* stream);
+/* torchvision resnet maxpool (3x3, stride 2, pad 1) on NHWC, resnet_ms.py:71 */
+int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
+                             int32_t dtype, void* stream);
+/* ya = relu(x*sa+ba), yb = relu(x*sb+bb): the eval BatchNorm+ReLU in front of feature_proj and
+ * feature_linear, fax_modules.py:281-292,379-384 (yb may be NULL) */
+int cobevt_bn_relu2(const void* x, const float* sa, const float* ba, void* ya, const float* sb,
+                    const float* bb, void* yb, int64_t rows, int32_t C, int32_t dtype, void* stream);
+/* normalised ray-direction embedding img_embed, fax_modules.py:346-358.
+ * I (NV,3,3) intrinsics (inverted in-kernel when invert_intrinsic, :500-501) or their inverse,
+ * E_inv (NV,4,4), w_img / w_cam (C,4) fp32 -> out (NV,h,w,C) */
+int cobevt_ray_embed(const float* I, const float* E_inv, const float* w_img, const float* w_cam,
+                     void* out, int32_t NV, int32_t h, int32_t w, float image_h, float image_w,
+                     int32_t C, int32_t invert_intrinsic, int32_t dtype, void* stream);
+/* out[b,n,p,:] = LayerNorm0( x[(b*P+p) % x_rows,:] + normalise(w_bev world_p + b_bev - w_cam c_{b,n}) )
+ * fax_modules.py:370-375,387-390 + the LayerNorm of to_q (:189); world (2,P) fp32 */
+int cobevt_bev_query(const void* x, int64_t x_rows, const float* world, const float* w_bev,
+                     const float* b_bev, const float* w_cam, const float* E_inv, void* out, int32_t BL,
+                     int32_t n, int32_t P, int32_t C, float eps, int32_t dtype, void* stream);
+/* row LayerNorm (gamma/beta NULL -> plain normalisation) */
+int cobevt_layernorm_rows(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
+                          int32_t C, float eps, int32_t dtype, void* stream);
+/* x (B,L,P,C) -> LayerNorm0(mean over L) (B,P,C): head of SwapFusionEncoder,
+ * swap_fusion_modules.py:275-278 */
+int cobevt_mean_views_ln(const void* x, void* y, int32_t B, int32_t L, int32_t P, int32_t C, float eps,
+                         int32_t dtype, void* stream);
+/* regroup (fuse_utils.py:8-61) + STTF bilinear warp (corpbevt.py:28-64) + ROI/cav mask
+ * (torch_transformation_utils.py:11-49) in one pass, no host sync:
+ * x (sum L, H, W, C), tm (B,L,4,4) fp32, record_len (B) int64 (device) ->
+ * out (B,L,H,W,C), mask (B,H,W,L) uint8 */
+int cobevt_sttf_regroup(const void* x, const float* tm, const int64_t* record_len, void* out,
+                        uint8_t* mask, int32_t B, int32_t L, int32_t H, int32_t W, int32_t C,
+                        float discrete_ratio, float downsample_rate, int32_t use_roi_mask,
+                        int32_t dtype, void* stream);
+/* NCHW <-> NHWC(Cpad) with dtype conversion; module API boundaries only */
+int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cpad,
+                   int32_t to_nhwc, int32_t src_dtype, int32_t dst_dtype, void* stream);
 
 #ifdef __cplusplus
 }
