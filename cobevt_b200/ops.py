@@ -14,6 +14,51 @@ F16, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 
 
+class _Stats:
+    """Launch / algorithmic-FLOP accounting per kernel family, and (profile mode) CUDA-event
+    timing of every launch on the launching stream.  bench.py reads this; nothing else does."""
+
+    def __init__(self):
+        self.reset()
+        self.profile = False
+
+    def reset(self):
+        self.launches = {"conv_gemm": 0, "window_attn": 0, "eltwise": 0}
+        self.flops = {"conv_gemm": 0, "window_attn": 0, "eltwise": 0}
+        self.events = []
+
+    def total_launches(self):
+        return sum(self.launches.values())
+
+    def family_ms(self):
+        out = {}
+        for fam, a, b in self.events:
+            out[fam] = out.get(fam, 0.0) + a.elapsed_time(b)
+        return out
+
+
+STATS = _Stats()
+
+
+class _timed:
+    def __init__(self, fam, flops=0):
+        self.fam, self.flops = fam, flops
+
+    def __enter__(self):
+        STATS.launches[self.fam] += 1
+        STATS.flops[self.fam] += self.flops
+        if STATS.profile:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if STATS.profile:
+            self.b.record()
+            STATS.events.append((self.fam, self.a, self.b))
+        return False
+
+
 def dtype_code(dt):
     if dt == torch.float16:
         return F16
@@ -59,6 +104,7 @@ class PackedConv:
         if cin_p != cin:
             w = torch.cat([w, torch.zeros(cout, cin_p - cin, kh, kw)], dim=1)
         self.cout, self.cin, self.kh, self.kw = cout, cin_p, kh, kw
+        self.k_alg = kh * kw * cin            # un-padded reduction length (algorithmic FLOPs)
         self.K = kh * kw * cin_p
         self.block_n = block_n or pick_block_n(cout)
         self.dtype = dtype
@@ -110,7 +156,8 @@ def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=
     p.ln_gamma, p.ln_beta = _ptr(ln_gamma), _ptr(ln_beta)
     p.in_upsample = 1 if in_upsample else 0
     p.act, p.dtype, p.block_n, p.ln_eps = act, dtype_code(x.dtype), pc.block_n, ln_eps
-    _lib.check(_lib.lib().cobevt_conv2d_nhwc_fwd(ctypes.byref(p), _stream()), "cobevt_conv2d_nhwc_fwd")
+    with _timed("conv_gemm", 2 * M * pc.k_alg * pc.cout):
+        _lib.check(_lib.lib().cobevt_conv2d_nhwc_fwd(ctypes.byref(p), _stream()), "cobevt_conv2d_nhwc_fwd")
     return y, y32, yln
 
 
@@ -169,7 +216,10 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p.qmap, p.kvmap = qmap, kvmap
     p.B, p.heads, p.q_mean, p.scale, p.dtype = B, heads, 1 if q_mean else 0, scale, dtype_code(q.dtype)
     p.q_stride, p.kv_stride, p.out_stride = qs, ks, C
-    _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
+    n_win = (qmap.H // qmap.w1) * (qmap.W // qmap.w2)
+    lq, lk = qmap.views * qmap.w1 * qmap.w2, kvmap.views * kvmap.w1 * kvmap.w2
+    with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32):
+        _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
     return out
 
 
@@ -184,7 +234,8 @@ def pack_rgb8(x, dtype):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3
     y = torch.empty(*x.shape[:-1], 8, dtype=dtype, device=x.device)
     npix = x.numel() // 3
-    _lib.check(_lib.lib().cobevt_pack_rgb8(_ptr(x), _ptr(y), npix, dtype_code(dtype), _stream()), "cobevt_pack_rgb8")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_pack_rgb8(_ptr(x), _ptr(y), npix, dtype_code(dtype), _stream()), "cobevt_pack_rgb8")
     return y
 
 
@@ -192,8 +243,9 @@ def maxpool3x3s2(x):
     N, H, W, C = x.shape
     OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(N, OH, OW, C, dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().cobevt_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), N, H, W, C, dtype_code(x.dtype), _stream()),
-               "cobevt_maxpool3x3s2_nhwc")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), N, H, W, C, dtype_code(x.dtype), _stream()),
+                   "cobevt_maxpool3x3s2_nhwc")
     return y
 
 
@@ -202,8 +254,9 @@ def bn_relu2(x, sa, ba, sb=None, bb=None):
     rows = x.numel() // C
     ya = torch.empty_like(x)
     yb = torch.empty_like(x) if sb is not None else None
-    _lib.check(_lib.lib().cobevt_bn_relu2(_ptr(x), _f32(sa), _f32(ba), _ptr(ya), _ptr(sb), _ptr(bb), _ptr(yb),
-                                          rows, C, dtype_code(x.dtype), _stream()), "cobevt_bn_relu2")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_bn_relu2(_ptr(x), _f32(sa), _f32(ba), _ptr(ya), _ptr(sb), _ptr(bb), _ptr(yb),
+                                              rows, C, dtype_code(x.dtype), _stream()), "cobevt_bn_relu2")
     return ya, yb
 
 
@@ -211,10 +264,11 @@ def ray_embed(I_inv, E_inv, w_img, w_cam, h, w, image_h, image_w, C, dtype, inve
     """I_inv: (NV,3,3) inverse intrinsics, or the intrinsics themselves with invert_intrinsic=True."""
     NV = I_inv.shape[0]
     out = torch.empty(NV, h, w, C, dtype=dtype, device=I_inv.device)
-    _lib.check(_lib.lib().cobevt_ray_embed(_f32(I_inv), _f32(E_inv), _f32(w_img), _f32(w_cam), _ptr(out), NV, h, w,
-                                           float(image_h), float(image_w), C, 1 if invert_intrinsic else 0,
-                                           dtype_code(dtype), _stream()),
-               "cobevt_ray_embed")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_ray_embed(_f32(I_inv), _f32(E_inv), _f32(w_img), _f32(w_cam), _ptr(out), NV, h, w,
+                                               float(image_h), float(image_w), C, 1 if invert_intrinsic else 0,
+                                               dtype_code(dtype), _stream()),
+                   "cobevt_ray_embed")
     return out
 
 
@@ -223,9 +277,10 @@ def bev_query(x, world, w_bev, b_bev, w_cam, E_inv, BL, n, P, eps=1e-5):
     C = x.shape[-1]
     x_rows = x.numel() // C
     out = torch.empty(BL, n, P, C, dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().cobevt_bev_query(_ptr(x), x_rows, _f32(world), _f32(w_bev), _f32(b_bev), _f32(w_cam),
-                                           _f32(E_inv), _ptr(out), BL, n, P, C, eps, dtype_code(x.dtype), _stream()),
-               "cobevt_bev_query")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_bev_query(_ptr(x), x_rows, _f32(world), _f32(w_bev), _f32(b_bev), _f32(w_cam),
+                                               _f32(E_inv), _ptr(out), BL, n, P, C, eps, dtype_code(x.dtype), _stream()),
+                   "cobevt_bev_query")
     return out
 
 
@@ -233,8 +288,9 @@ def layernorm_rows(x, gamma=None, beta=None, eps=1e-5):
     C = x.shape[-1]
     assert x.is_contiguous()
     y = torch.empty_like(x)
-    _lib.check(_lib.lib().cobevt_layernorm_rows(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, eps,
-                                                dtype_code(x.dtype), _stream()), "cobevt_layernorm_rows")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_layernorm_rows(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, eps,
+                                                    dtype_code(x.dtype), _stream()), "cobevt_layernorm_rows")
     return y
 
 
@@ -242,8 +298,9 @@ def mean_views_ln(x, eps=1e-5):
     """x (B, L, P, C) -> (B, P, C)."""
     B, L, P, C = x.shape
     y = torch.empty(B, P, C, dtype=x.dtype, device=x.device)
-    _lib.check(_lib.lib().cobevt_mean_views_ln(_ptr(x), _ptr(y), B, L, P, C, eps, dtype_code(x.dtype), _stream()),
-               "cobevt_mean_views_ln")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_mean_views_ln(_ptr(x), _ptr(y), B, L, P, C, eps, dtype_code(x.dtype), _stream()),
+                   "cobevt_mean_views_ln")
     return y
 
 
@@ -253,9 +310,10 @@ def sttf_regroup(x, tm, record_len, B, L, discrete_ratio, downsample_rate, use_r
     assert tm.dtype == torch.float32 and tm.is_contiguous() and record_len.dtype == torch.int64
     out = torch.empty(B, L, H, W, C, dtype=x.dtype, device=x.device)
     mask = torch.empty(B, H, W, L, dtype=torch.uint8, device=x.device)
-    _lib.check(_lib.lib().cobevt_sttf_regroup(_ptr(x), _ptr(tm), _ptr(record_len), _ptr(out), _ptr(mask), B, L, H, W, C,
-                                              float(discrete_ratio), float(downsample_rate), 1 if use_roi_mask else 0,
-                                              dtype_code(x.dtype), _stream()), "cobevt_sttf_regroup")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_sttf_regroup(_ptr(x), _ptr(tm), _ptr(record_len), _ptr(out), _ptr(mask), B, L, H, W, C,
+                                                  float(discrete_ratio), float(downsample_rate), 1 if use_roi_mask else 0,
+                                                  dtype_code(x.dtype), _stream()), "cobevt_sttf_regroup")
     return out, mask
 
 
@@ -269,8 +327,9 @@ def nchw_to_nhwc(x, dtype, cpad=None):
     N, C, H, W = x.shape
     cp = cpad or C
     y = torch.empty(N, H, W, cp, dtype=dtype, device=x.device)
-    _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 1, _any_code(x.dtype), _any_code(dtype), _stream()),
-               "cobevt_permute")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 1, _any_code(x.dtype), _any_code(dtype), _stream()),
+                   "cobevt_permute")
     return y
 
 
@@ -280,6 +339,7 @@ def nhwc_to_nchw(x, dtype, c=None):
     N, H, W, cp = x.shape
     C = c or cp
     y = torch.empty(N, C, H, W, dtype=dtype, device=x.device)
-    _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 0, _any_code(x.dtype), _any_code(dtype), _stream()),
-               "cobevt_permute")
+    with _timed("eltwise"):
+        _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 0, _any_code(x.dtype), _any_code(dtype), _stream()),
+                   "cobevt_permute")
     return y

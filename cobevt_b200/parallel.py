@@ -1,0 +1,104 @@
+"""Agent-row sharding of the CoBEVT forward across the GPUs of one node.
+
+Encoder + SinBEVT treat every agent (with its cameras) as an independent batch row, so rows
+are split contiguously over ranks.  FuseBEVT is the only place agents of one sample meet:
+each rank all-gathers the per-agent BEV tiles (rows x 32 x 32 x 128 16-bit, <= 256 KiB/row --
+latency-bound, so a plain NCCL all-gather on the compute stream) and then runs
+regroup/STTF -> FuseBEVT -> decoder -> head for the contiguous block of samples it owns.
+When no sample straddles a rank boundary the exchange is skipped entirely.
+
+The compute steps are injected (``encode`` / ``fuse``) so the same plumbing is exercised by
+the world_size-2 gloo tests on CPU with the oracle's math standing in for the kernels.
+"""
+import torch
+import torch.distributed as dist
+
+
+def row_shard(total_rows, world, rank):
+    """Contiguous equal split (first ranks take the remainder)."""
+    base, rem = divmod(total_rows, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def sample_shard(n_samples, world, rank):
+    return row_shard(n_samples, world, rank)
+
+
+def needs_exchange(record_len, world):
+    """True if some sample's agent rows live on more than one rank, or a rank owns a sample
+    whose rows another rank encoded."""
+    total = sum(record_len)
+    starts = [0]
+    for n in record_len:
+        starts.append(starts[-1] + n)
+    for r in range(world):
+        r0, r1 = row_shard(total, world, r)
+        s0, s1 = sample_shard(len(record_len), world, r)
+        if (starts[s0], starts[s1]) != (r0, r1):
+            return True
+    return False
+
+
+def sharded_forward(encode, fuse, local_inputs, record_len, rank, world, group=None):
+    """encode(local_inputs) -> (rows_local, ...) BEV tiles for this rank's rows;
+    fuse(tiles_of_owned_samples, sample_start, sample_end) -> output for the owned samples.
+    ``record_len`` is the GLOBAL host-side list of agents per sample (no device sync)."""
+    total = sum(record_len)
+    r0, r1 = row_shard(total, world, rank)
+    tiles = encode(local_inputs)
+    assert tiles.shape[0] == r1 - r0, (tiles.shape, r0, r1)
+    s0, s1 = sample_shard(len(record_len), world, rank)
+    starts = [0]
+    for n in record_len:
+        starts.append(starts[-1] + n)
+    if world > 1 and needs_exchange(record_len, world):
+        rmax = -(-total // world)
+        if tiles.shape[0] < rmax:                      # equalise for all_gather_into_tensor
+            pad = torch.zeros(rmax - tiles.shape[0], *tiles.shape[1:], dtype=tiles.dtype, device=tiles.device)
+            tiles = torch.cat([tiles, pad], 0)
+        gathered = torch.empty(world * rmax, *tiles.shape[1:], dtype=tiles.dtype, device=tiles.device)
+        dist.all_gather_into_tensor(gathered, tiles.contiguous(), group=group)
+        if total % world:                              # drop the per-rank padding rows
+            parts = []
+            for r in range(world):
+                a, b = row_shard(total, world, r)
+                parts.append(gathered[r * rmax: r * rmax + (b - a)])
+            gathered = torch.cat(parts, 0)
+        owned = gathered[starts[s0]: starts[s1]]
+    else:
+        owned = tiles[starts[s0] - r0: starts[s1] - r0]
+    return fuse(owned, s0, s1)
+
+
+class ShardedCorpBEVT:
+    """CorpBEVT (modules.py) run agent-row-sharded over a process group."""
+
+    def __init__(self, model, rank=0, world=1, group=None):
+        self.m, self.rank, self.world, self.group = model, rank, world, group
+
+    def __call__(self, local_batch, record_len, transformation_matrix):
+        """local_batch: this rank's rows of inputs/intrinsic/extrinsic; record_len: global
+        python list; transformation_matrix: global (B, max_cav, 4, 4) tensor (replicated)."""
+        from . import ops
+        m = self.m
+        n_cams = local_batch['inputs'].shape[2]
+
+        def encode(lb):
+            feats = m.encoder.features_nhwc(lb['inputs'])
+            feats = [feats[i] for i in m.encoder.idx_pick]
+            return m.fax.run_nhwc(feats, n_cams, lb['intrinsic'], lb['extrinsic'])
+
+        def fuse(tiles, s0, s1):
+            if s1 <= s0:
+                return None
+            dev = tiles.device
+            rl = torch.tensor(record_len[s0:s1], dtype=torch.int64, device=dev)
+            tm = transformation_matrix[s0:s1].to(device=dev, dtype=torch.float32).contiguous()
+            y, mask = ops.sttf_regroup(tiles.contiguous(), tm, rl, s1 - s0, m.max_cav, m.discrete_ratio,
+                                       m.downsample_rate, m.use_roi_mask)
+            y = m.fusion_net.run_nhwc(y, mask)
+            y = m.decoder.plan().run(y)
+            return m.seg_head.plan().run(y, s1 - s0, 1)
+
+        return sharded_forward(encode, fuse, local_batch, record_len, self.rank, self.world, self.group)
