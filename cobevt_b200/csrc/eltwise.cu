@@ -152,19 +152,15 @@ __global__ void bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __r
 }
 
 // ------------------------------------------------------------------ ray-direction embedding
-// one warp per feature cell; out = normalize(W_img d - W_cam c)   (fax_modules.py:346-358)
-__global__ void ray_embed_kernel(const float* __restrict__ I_inv, const float* __restrict__ E_inv,
+// out = normalize(W_img d - W_cam c)   (fax_modules.py:346-358).  blockIdx.y = view; every lane
+// keeps the embedding weights of its C/32 channels in registers and the warp walks over cells.
+constexpr int CELLS_PER_BLOCK = 256;
+__global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict__ I_inv, const float* __restrict__ E_inv,
                                  const float* __restrict__ w_img, const float* __restrict__ w_cam,
                                  uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
                                  int C, int invert_I, int bf16) {
-  const int lane = threadIdx.x & 31;
-  const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (cell >= (int64_t)NV * h * w) return;
-  const int ix = (int)(cell % w);
-  const int iy = (int)((cell / w) % h);
-  const int v = (int)(cell / ((int64_t)w * h));
-  const float px = (w > 1 ? (float)ix / (float)(w - 1) : 0.f) * image_w;
-  const float py = (h > 1 ? (float)iy / (float)(h - 1) : 0.f) * image_h;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.y;
   float Ii[9];
 #pragma unroll
   for (int r = 0; r < 9; ++r) Ii[r] = I_inv[v * 9 + r];
@@ -176,64 +172,107 @@ __global__ void ray_embed_kernel(const float* __restrict__ I_inv, const float* _
     Ii[3] = B * idet;  Ii[4] = (a * k - c_ * g) * idet;    Ii[5] = -(a * f - c_ * d_) * idet;
     Ii[6] = Cc * idet; Ii[7] = -(a * hh - b_ * g) * idet;  Ii[8] = (a * e_ - b_ * d_) * idet;
   }
-  const float* Ei = E_inv + v * 16;
-  const float cx = Ii[0] * px + Ii[1] * py + Ii[2];
-  const float cy = Ii[3] * px + Ii[4] * py + Ii[5];
-  const float cz = Ii[6] * px + Ii[7] * py + Ii[8];
-  float d[4], c[4];
+  float Ei[16];
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    d[r] = Ei[r * 4] * cx + Ei[r * 4 + 1] * cy + Ei[r * 4 + 2] * cz + Ei[r * 4 + 3];
-    c[r] = Ei[r * 4 + 3];
-  }
+  for (int r = 0; r < 16; ++r) Ei[r] = E_inv[v * 16 + r];
   const int per = C / 32;
-  float e[MAXC_PER_LANE];
-  float ss = 0.f;
-  for (int i = 0; i < per; ++i) {
-    const int ch = lane * per + i;
-    float a = 0.f;
+  float wi[MAXC_PER_LANE][4], ce[MAXC_PER_LANE];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) a += w_img[ch * 4 + r] * d[r] - w_cam[ch * 4 + r] * c[r];
-    e[i] = a;
-    ss += a * a;
+  for (int i = 0; i < MAXC_PER_LANE; ++i) {
+    if (i < per) {
+      const int ch = lane * per + i;
+      float cacc = 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) { wi[i][r] = w_img[ch * 4 + r]; cacc += w_cam[ch * 4 + r] * Ei[r * 4 + 3]; }
+      ce[i] = cacc;
+    }
   }
-  const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
-  for (int i = 0; i < per; ++i) e[i] *= inv;
-  store_row(out + cell * C, C, lane, bf16, e);
+  const int ncell = h * w;
+  const int base = blockIdx.x * CELLS_PER_BLOCK;
+  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 8) {
+    const int cell = base + cc;
+    if (cell >= ncell) break;
+    const int ix = cell % w, iy = cell / w;
+    const float px = (w > 1 ? (float)ix / (float)(w - 1) : 0.f) * image_w;
+    const float py = (h > 1 ? (float)iy / (float)(h - 1) : 0.f) * image_h;
+    const float cx = Ii[0] * px + Ii[1] * py + Ii[2];
+    const float cy = Ii[3] * px + Ii[4] * py + Ii[5];
+    const float cz = Ii[6] * px + Ii[7] * py + Ii[8];
+    float d[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) d[r] = Ei[r * 4] * cx + Ei[r * 4 + 1] * cy + Ei[r * 4 + 2] * cz + Ei[r * 4 + 3];
+    float e[MAXC_PER_LANE];
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) {
+      if (i < per) {
+        const float a = wi[i][0] * d[0] + wi[i][1] * d[1] + wi[i][2] * d[2] + wi[i][3] * d[3] - ce[i];
+        e[i] = a;
+        ss += a * a;
+      }
+    }
+    const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) e[i] *= inv;
+    store_row(out + ((int64_t)v * ncell + cell) * C, C, lane, bf16, e);
+  }
 }
 
 // ------------------------------------------------------------------ BEV positional query
 // out[b, n, p, :] = LN0( x[b, p, :] + normalize(W_bev world_p + b_bev - W_cam c_{b,n}) )
-// (fax_modules.py:370-375,387-390 followed by the LayerNorm of to_q, :189,216)
-__global__ void bev_query_kernel(const uint16_t* __restrict__ x, int64_t x_rows, const float* __restrict__ world,
+// (fax_modules.py:370-375,387-390 followed by the LayerNorm of to_q, :189,216).
+// blockIdx.y = b*n + view; lanes keep their channels' weights in registers.
+__global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restrict__ x, int64_t x_rows, const float* __restrict__ world,
                                  const float* __restrict__ w_bev, const float* __restrict__ b_bev,
                                  const float* __restrict__ w_cam, const float* __restrict__ E_inv,
                                  uint16_t* __restrict__ out, int BL, int n, int P, int C, float eps, int bf16) {
-  const int lane = threadIdx.x & 31;
-  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (row >= (int64_t)BL * n * P) return;
-  const int p = (int)(row % P);
-  const int v = (int)(row / P);        // b * n + view
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int v = blockIdx.y;
   const int b = v / n;
-  const float wx = world[p], wy = world[P + p];
   const float* Ei = E_inv + (int64_t)v * 16;
   const float c0 = Ei[3], c1 = Ei[7], c2 = Ei[11], c3 = Ei[15];
   const int per = C / 32;
-  float e[MAXC_PER_LANE], xv[MAXC_PER_LANE];
-  float ss = 0.f;
-  for (int i = 0; i < per; ++i) {
-    const int ch = lane * per + i;
-    const float a = w_bev[ch * 2] * wx + w_bev[ch * 2 + 1] * wy + b_bev[ch] -
-                    (w_cam[ch * 4] * c0 + w_cam[ch * 4 + 1] * c1 + w_cam[ch * 4 + 2] * c2 + w_cam[ch * 4 + 3] * c3);
-    e[i] = a;
-    ss += a * a;
+  float wb[MAXC_PER_LANE][2], ce[MAXC_PER_LANE];
+#pragma unroll
+  for (int i = 0; i < MAXC_PER_LANE; ++i) {
+    if (i < per) {
+      const int ch = lane * per + i;
+      wb[i][0] = w_bev[ch * 2];
+      wb[i][1] = w_bev[ch * 2 + 1];
+      ce[i] = b_bev[ch] - (w_cam[ch * 4] * c0 + w_cam[ch * 4 + 1] * c1 + w_cam[ch * 4 + 2] * c2 + w_cam[ch * 4 + 3] * c3);
+    }
   }
-  const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
-  const int64_t xr = ((int64_t)b * P + p) % x_rows;
-  load_row(x + xr * C, C, lane, bf16, xv);
-  for (int i = 0; i < per; ++i) e[i] = fmaf(e[i], inv, xv[i]);
-  ln_row(e, per, C, lane, eps, nullptr, nullptr);
-  store_row(out + row * C, C, lane, bf16, e);
+  const int base = blockIdx.x * CELLS_PER_BLOCK;
+  const float invC = 1.0f / (float)C;
+  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 8) {
+    const int p = base + cc;
+    if (p >= P) break;
+    const float wx = world[p], wy = world[P + p];
+    float e[MAXC_PER_LANE], xv[MAXC_PER_LANE];
+    const int64_t xr = ((int64_t)b * P + p) % x_rows;
+    load_row(x + xr * C, C, lane, bf16, xv);
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) {
+      if (i < per) {
+        const float a = fmaf(wb[i][0], wx, fmaf(wb[i][1], wy, ce[i]));
+        e[i] = a;
+        ss += a * a;
+      }
+    }
+    const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
+    float s1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) { e[i] = fmaf(e[i], inv, xv[i]); s1 += e[i]; }
+    const float mean = warp_sum(s1) * invC;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) { const float dd = e[i] - mean; s2 += dd * dd; }
+    const float rstd = rsqrtf(warp_sum(s2) * invC + eps);
+#pragma unroll
+    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) e[i] = (e[i] - mean) * rstd;
+    store_row(out + ((int64_t)v * P + p) * C, C, lane, bf16, e);
+  }
 }
 
 // ------------------------------------------------------------------ LayerNorm over rows
@@ -408,8 +447,8 @@ extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const fl
                                  int32_t NV, int32_t h, int32_t w, float image_h, float image_w, int32_t C,
                                  int32_t invert_intrinsic, int32_t dtype, void* stream) {
   if (!I_inv || !E_inv || !w_img || !w_cam || !out || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "ray_embed: bad args (C must be 64/128/256)");
-  const int64_t threads = (int64_t)NV * h * w * 32;
-  ray_embed_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w,
+  dim3 grid((h * w + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, NV);
+  ray_embed_kernel<<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w,
                                                                      image_h, image_w, C, invert_intrinsic, dtype);
   return cobevt::check_launch("ray_embed");
 }
@@ -419,8 +458,8 @@ extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* worl
                                  int32_t C, float eps, int32_t dtype, void* stream) {
   if (!x || !world || !w_bev || !b_bev || !w_cam || !E_inv || !out || !ok_c(C) || x_rows <= 0)
     return fail(COBEVT_ERR_SHAPE, "bev_query: bad args");
-  const int64_t threads = (int64_t)BL * n * P * 32;
-  bev_query_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam,
+  dim3 grid((P + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, BL * n);
+  bev_query_kernel<<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam,
                                                                      E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   return cobevt::check_launch("bev_query");
 }

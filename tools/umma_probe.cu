@@ -22,6 +22,7 @@ struct ProbeArgs {
   uint32_t a_koff[32];                // byte offset of A start per k-step
   uint32_t b_koff[32];
   uint32_t use_bulk;                  // 1: load images with cp.async.bulk
+  uint32_t a_base_off[32];            // descriptor base_offset field per k-step (bits 49..51)
 };
 
 __global__ void __launch_bounds__(128, 1)
@@ -67,7 +68,7 @@ probe_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_im
   if (tid == 0) {
     tc_fence_after_sync();
     for (uint32_t ks = 0; ks < args.nk; ++ks) {
-      uint64_t da = make_smem_desc(smem_u32(sa) + args.a_koff[ks], args.a_lbo, args.a_sbo, args.a_layout);
+      uint64_t da = make_smem_desc(smem_u32(sa) + args.a_koff[ks], args.a_lbo, args.a_sbo, args.a_layout) | ((uint64_t)(args.a_base_off[ks] & 7u) << 49);
       uint64_t db = make_smem_desc(smem_u32(sb) + args.b_koff[ks], args.b_lbo, args.b_sbo, args.b_layout);
       umma_f16(tmem_base, da, db, args.idesc, ks > 0 ? 1u : 0u);
     }
@@ -348,5 +349,67 @@ int main(int argc, char** argv) {
     run_case("sw128 K-major f16 N=128 K=192", M, N, K, false, pA, M * K * 2, pA, N * K * 2, a);
   }
   ++id;
+
+  // ---- strip cases: A rows live in a contiguous strip, swizzled by ABSOLUTE smem address;
+  //      the tile for "tap j" starts j rows (j*128 B) into the strip.  hyp 0: base_offset = j,
+  //      hyp 1: base_offset = 0.
+  for (int j = 1; j <= 3; j += 2)
+    for (int hyp = 0; hyp < 2; ++hyp, ++id) {
+      if (!want(id)) continue;
+      const uint32_t M = 128, N = 64, K = 64;
+      ProbeArgs a{};
+      a.a_layout = LAYOUT_SW128; a.a_lbo = 16; a.a_sbo = 1024;
+      a.b_layout = LAYOUT_SW128; a.b_lbo = 16; a.b_sbo = 1024;
+      a.idesc = make_idesc_f16(M, N, false, false, false);
+      for (uint32_t ks = 0; ks < K / 16; ++ks) {
+        a.a_koff[ks] = j * 128 + ks * 32; a.b_koff[ks] = ks * 32;
+        a.a_base_off[ks] = hyp == 0 ? (uint32_t)j : 0u;
+      }
+      auto pA = [=](uint32_t r, uint32_t k) { uint32_t row = r + j; return row * 128u + ((((k / 8) ^ (row & 7u))) << 4) + (k % 8) * 2; };
+      auto pB = [=](uint32_t r, uint32_t k) { return sw128(r, k / 8) + (k % 8) * 2; };
+      char nm[96]; snprintf(nm, 96, "strip: start +%d rows, base_offset=%s", j, hyp == 0 ? "j" : "0");
+      run_case(nm, M, N, K, false, pA, (M + 8) * 128, pB, N * K * 2, a);
+    }
+  // ---- 2-D halo tile: 18 x 16-pixel pitch, output tile 16 rows x 8 px; tap (ky,kx) starts at
+  //      (ky*16 + kx) rows; SBO = 16*128 = 2048.
+  for (int tap = 0; tap < 3; ++tap)
+    for (int hyp = 0; hyp < 2; ++hyp, ++id) {
+      if (!want(id)) continue;
+      const int ky = tap, kx = tap;   // (0,0) (1,1) (2,2)
+      const uint32_t M = 128, N = 64, K = 64;
+      ProbeArgs a{};
+      a.a_layout = LAYOUT_SW128; a.a_lbo = 16; a.a_sbo = 2048;
+      a.b_layout = LAYOUT_SW128; a.b_lbo = 16; a.b_sbo = 1024;
+      a.idesc = make_idesc_f16(M, N, false, false, false);
+      const uint32_t start_row = ky * 16 + kx;
+      for (uint32_t ks = 0; ks < K / 16; ++ks) {
+        a.a_koff[ks] = start_row * 128 + ks * 32; a.b_koff[ks] = ks * 32;
+        a.a_base_off[ks] = hyp == 0 ? (start_row & 7u) : 0u;
+      }
+      // logical A row r = (gy = r / 8, gx = r % 8) -> halo row (ky + gy) * 16 + kx + gx
+      auto pA = [=](uint32_t r, uint32_t k) { uint32_t row = (ky + r / 8) * 16 + kx + (r % 8); return row * 128u + ((((k / 8) ^ (row & 7u))) << 4) + (k % 8) * 2; };
+      auto pB = [=](uint32_t r, uint32_t k) { return sw128(r, k / 8) + (k % 8) * 2; };
+      char nm[96]; snprintf(nm, 96, "halo 18x16: tap (%d,%d), SBO 2048, base_offset=%s", ky, kx, hyp == 0 ? "row&7" : "0");
+      run_case(nm, M, N, K, false, pA, 18 * 16 * 128, pB, N * K * 2, a);
+    }
+  // ---- halo with pitch 10 pixels (SBO = 1280, groups have different swizzle phases)
+  for (int hyp = 0; hyp < 2; ++hyp, ++id) {
+    if (!want(id)) continue;
+    const int ky = 1, kx = 1;
+    const uint32_t M = 128, N = 64, K = 64;
+    ProbeArgs a{};
+    a.a_layout = LAYOUT_SW128; a.a_lbo = 16; a.a_sbo = 1280;
+    a.b_layout = LAYOUT_SW128; a.b_lbo = 16; a.b_sbo = 1024;
+    a.idesc = make_idesc_f16(M, N, false, false, false);
+    const uint32_t start_row = ky * 10 + kx;
+    for (uint32_t ks = 0; ks < K / 16; ++ks) {
+      a.a_koff[ks] = start_row * 128 + ks * 32; a.b_koff[ks] = ks * 32;
+      a.a_base_off[ks] = hyp == 0 ? (start_row & 7u) : 0u;
+    }
+    auto pA = [=](uint32_t r, uint32_t k) { uint32_t row = (ky + r / 8) * 10 + kx + (r % 8); return row * 128u + ((((k / 8) ^ (row & 7u))) << 4) + (k % 8) * 2; };
+    auto pB = [=](uint32_t r, uint32_t k) { return sw128(r, k / 8) + (k % 8) * 2; };
+    char nm[96]; snprintf(nm, 96, "halo pitch 10 (SBO 1280), base_offset=%s", hyp == 0 ? "row&7" : "0");
+    run_case(nm, M, N, K, false, pA, 18 * 10 * 128 + 1024, pB, N * K * 2, a);
+  }
   return 0;
 }
