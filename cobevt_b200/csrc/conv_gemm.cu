@@ -1,24 +1,35 @@
-// Implicit-GEMM convolution / token GEMM for sm_100a.
+// Implicit-GEMM convolution / token GEMM for sm_100a -- persistent, warp-specialised.
 //
 //   D[128 x BN] (TMEM, fp32) = A[128 x K] * B[BN x K]^T,   K = KH*KW*Cin
 //
-//   A : gathered on the fly from the NHWC activation (no im2col buffer): 128 producer
-//       threads issue 16-byte cp.async (zero-fill outside the image) straight into a
-//       K-major SWIZZLE_128B stage, 8 lanes per 128-byte channel run -> coalesced.
-//   B : weights pre-packed on the host as ready-made SWIZZLE_128B tile images; one
-//       cp.async.bulk (TMA engine) per stage, completing on the stage's mbarrier.
-//   MMA : one thread issues tcgen05.mma (M=128, N=BN, K=16) x4 per 64-wide k-block;
-//       tcgen05.commit releases the stage / signals the epilogue.
-//   Epilogue : 4 warps, one TMEM lane (= output row) per thread: +bias, +residual,
-//       ReLU/GELU, optional row LayerNorm-normalised second output, 16-bit / fp32 stores.
+// One CTA per SM walks over output tiles (128 rows x BN channels).  Warp roles:
+//   warps 0-3  A producers   16-byte cp.async (zero-fill outside the image) into K-major
+//                            SWIZZLE_128B stages; 8 lanes per 128-byte channel run (coalesced)
+//   warps 4-7  epilogue      one TMEM lane (= output row) per thread: +bias, +residual, ReLU /
+//                            GELU, optional row LayerNorm second output, 16-bit / fp32 stores;
+//                            the accumulator is double-buffered in TMEM so the epilogue of tile i
+//                            overlaps the main loop of tile i+1
+//   warp  8    B loader      weights pre-packed on the host as ready SWIZZLE_128B tile images,
+//                            one cp.async.bulk (TMA engine) per k-block, or ALL k-blocks once when
+//                            they fit (resident weights: token GEMMs and 64-channel convs)
+//   warp  9    MMA issuer    one thread, tcgen05.mma M=128 N=BN K=16; tcgen05.commit frees stages
 //
-// Replaces the cuDNN/cuBLAS calls behind torchvision ResNet (resnet_ms.py:46-89), the
-// FAX Bottleneck/downsample convs (fax_modules.py:472-489) and every nn.Linear of the
-// token path (see include/cobevt_b200.h).
+// A-operand modes
+//   GATHER  any conv: per 64-wide k-block the 128 x 64 im2col slice is gathered from the NHWC
+//           activation (no im2col buffer in HBM).
+//   HALO    3x3 / stride 1 / pad 1 / Cin % 64 == 0 (the bulk of the ResNet encoder): the output
+//           tile is 16 rows x 8 pixels; its 18 x 10 x 64ch input halo is loaded ONCE per 64-channel
+//           slab and all nine taps read it in place through shifted UMMA descriptors (start =
+//           slab + (ky*10+kx)*128 B, stride-byte-offset = 10*128 B).  The SWIZZLE_128B XOR is a
+//           function of absolute smem address bits (profiles/r01_umma_probe_halo.log), so shifted
+//           starts need no re-layout.  L2->SM traffic for A drops 9x vs the gather.
+//
+// Replaces the cuDNN/cuBLAS calls behind torchvision ResNet (resnet_ms.py:46-89), the FAX
+// Bottleneck/downsample convs (fax_modules.py:472-489) and every nn.Linear of the token path
+// (see include/cobevt_b200.h).
 #include "sm100.cuh"
 #include "common.h"
 #include <cstring>
-#include <vector>
 
 using namespace sm100;
 
@@ -26,42 +37,26 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
-constexpr int NUM_PRODUCERS = 128;
-constexpr int NUM_THREADS = 256;
-constexpr int LAG = 2;  // cp.async groups kept in flight per producer thread
-constexpr int kMaxDynSmem = 227 * 1024 - 2048;  // static smem (barriers) counts against the 227 KB
+constexpr int A_GATHER_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
+constexpr int A_HALO_BYTES = 24 * 1024;                // 180 rows x 128 B = 23040, padded to 1 KB multiple
+constexpr int NUM_THREADS = 320;
+constexpr int kMaxDynSmem = 227 * 1024 - 2048;         // static smem (barriers) counts against 227 KB
+constexpr int MAX_STAGES = 8;
 
-template <int BN>
-struct Cfg {
-  static constexpr int kStages = (BN == 128) ? 3 : 4;
-  static constexpr int kBStage = BN * BLOCK_K * 2;
-  static constexpr int kStageBytes = A_STAGE_BYTES + kBStage;
-  static constexpr int kTmemCols = BN < 32 ? 32 : BN;
-  static constexpr int kMinBlocks = (BN == 256) ? 1 : 2;
-};
-
-struct RowInfo {
-  int32_t pixbase;  // n * Hin * Win
-  int32_t iy0, ix0; // top-left logical input coordinate of the receptive field
-  int32_t valid;
-};
-struct ChunkInfo {
-  int16_t ky, kx;
-  int16_t coff;
-  int16_t valid;
-};
+enum { MODE_GATHER = 0, MODE_HALO = 1 };
 
 struct KArgs {
   CobevtConvParams p;
-  int32_t M, K, KB, n_tiles;
+  int32_t M, K, KB, n_tiles, m_tiles, total_tiles;
+  int32_t mode, sa, sb, resident_b;
+  int32_t tiles_y, tiles_x, nslab;      // HALO geometry
   uint32_t idesc;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
 }
-
 __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   if (bf16) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -75,65 +70,55 @@ __device__ __forceinline__ float2 unpack2(uint32_t u, int bf16) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
+// output row (TMEM lane) -> linear output pixel index, or -1
+__device__ __forceinline__ int64_t out_row_index(const KArgs& a, int m_tile, int row) {
+  const CobevtConvParams& p = a.p;
+  if (a.mode == MODE_HALO) {
+    const int per_img = a.tiles_y * a.tiles_x;
+    const int n = m_tile / per_img;
+    const int t = m_tile - n * per_img;
+    const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+    const int oy = ty * TILE_H + (row >> 3), ox = tx * TILE_W + (row & 7);
+    if (oy >= p.OH || ox >= p.OW) return -1;
+    return ((int64_t)n * p.OH + oy) * p.OW + ox;
+  }
+  const int64_t m = (int64_t)m_tile * BLOCK_M + row;
+  return m < a.M ? m : -1;
+}
+
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, Cfg<BN>::kMinBlocks)
-conv_gemm_kernel(const KArgs a) {
-  using C = Cfg<BN>;
-  constexpr int S = C::kStages;
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a) {
+  constexpr int kBStage = BN * BLOCK_K * 2;
+  constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [stages: A|B] [row table] [chunk table] [barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  RowInfo* rows = reinterpret_cast<RowInfo*>(smem + S * C::kStageBytes);
-  ChunkInfo* chunks = reinterpret_cast<ChunkInfo*>(rows + BLOCK_M);
-  __shared__ uint64_t full_bar[S], empty_bar[S], tmem_full_bar;
+  const int SA = a.sa, SB = a.sb;
+  const int a_stage_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + SA * a_stage_bytes;
+  __shared__ uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES];
+  __shared__ uint64_t acc_full[2], acc_empty[2], b_res_full;
   __shared__ uint32_t tmem_base_s;
 
   const CobevtConvParams& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_tile = blockIdx.x % a.n_tiles;
-  const int m_tile = blockIdx.x / a.n_tiles;
   const int KB = a.KB;
-  const int Hlog = p.in_upsample ? p.Hin * 2 : p.Hin;
-  const int Wlog = p.in_upsample ? p.Win * 2 : p.Win;
 
-  // ---- one-time setup -------------------------------------------------------
   if (tid == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], NUM_PRODUCERS + 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < MAX_STAGES; ++s) {
+      mbar_init(&a_full[s], 128);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
-    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&b_res_full, 1);
     mbar_fence_init();
   }
   if (warp == 4) {
-    tmem_alloc(&tmem_base_s, C::kTmemCols);
+    tmem_alloc(&tmem_base_s, kTmemCols);
     tmem_relinquish();
-  }
-  if (tid < BLOCK_M) {
-    const int m = m_tile * BLOCK_M + tid;
-    RowInfo ri;
-    ri.valid = m < a.M;
-    const int mm = ri.valid ? m : 0;
-    const int ohw = p.OH * p.OW;
-    const int n = mm / ohw;
-    const int rem = mm - n * ohw;
-    const int oy = rem / p.OW, ox = rem - oy * p.OW;
-    ri.pixbase = n * p.Hin * p.Win;
-    ri.iy0 = oy * p.stride_h - p.pad_h;
-    ri.ix0 = ox * p.stride_w - p.pad_w;
-    rows[tid] = ri;
-  }
-  for (int q = tid; q < KB * 8; q += NUM_THREADS) {
-    const int k = q * 8;
-    ChunkInfo ci;
-    ci.valid = k < a.K;
-    const int kk = ci.valid ? k : 0;
-    const int tap = kk / p.Cin;
-    ci.coff = (int16_t)(kk - tap * p.Cin);
-    ci.ky = (int16_t)(tap / p.KW);
-    ci.kx = (int16_t)(tap - ci.ky * p.KW);
-    chunks[q] = ci;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -141,236 +126,390 @@ conv_gemm_kernel(const KArgs a) {
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp < 4) {
-    // =========================== A producers ================================
-    const int c8 = tid & 7;
-    const int r0 = tid >> 3;
-    int pixbase[8], iy0[8], ix0[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const RowInfo ri = rows[r0 + 16 * i];
-      pixbase[i] = ri.pixbase;
-      iy0[i] = ri.valid ? ri.iy0 : -(1 << 28);
-      ix0[i] = ri.ix0;
-    }
+    // ================================ A producers ========================================
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
-    for (int kb = 0; kb < KB; ++kb) {
-      const int s = kb % S;
-      const uint32_t ph = (kb / S) & 1;
-      mbar_wait(&empty_bar[s], ph ^ 1u);
-      const ChunkInfo ci = chunks[kb * 8 + c8];
-      uint8_t* sA = stage_base + s * C::kStageBytes;
+    uint32_t it = 0;   // stage uses issued so far (across tiles)
+    constexpr int LAG = 2;
+    if (a.mode == MODE_GATHER) {
+      const int Hlog = p.in_upsample ? p.Hin * 2 : p.Hin;
+      const int Wlog = p.in_upsample ? p.Win * 2 : p.Win;
+      const int c8 = tid & 7, r0 = tid >> 3;
+      const int ohw = p.OH * p.OW;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles;
+        int pixbase[8], iy0[8], ix0[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
-        int iy = iy0[i] + ci.ky, ix = ix0[i] + ci.kx;
-        const bool ok = ci.valid && iy >= 0 && iy < Hlog && ix >= 0 && ix < Wlog;
-        if (p.in_upsample) { iy >>= 1; ix >>= 1; }
-        const int64_t off = ((int64_t)(pixbase[i] + iy * p.Win + ix) * p.Cin + ci.coff) * 2;
-        cp_async16(sA + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
+        for (int i = 0; i < 8; ++i) {
+          const int m = m_tile * BLOCK_M + r0 + 16 * i;
+          const bool ok = m < a.M;
+          const int mm = ok ? m : 0;
+          const int n = mm / ohw;
+          const int rem = mm - n * ohw;
+          const int oy = rem / p.OW, ox = rem - oy * p.OW;
+          pixbase[i] = n * p.Hin * p.Win;
+          iy0[i] = ok ? oy * p.stride_h - p.pad_h : -(1 << 28);
+          ix0[i] = ox * p.stride_w - p.pad_w;
+        }
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % SA;
+          mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1u);
+          // chunk -> (tap, channel offset)
+          const int k = kb * BLOCK_K + c8 * 8;
+          const bool kvalid = k < a.K;
+          const int kk = kvalid ? k : 0;
+          const int tap = kk / p.Cin;
+          const int coff = kk - tap * p.Cin;
+          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          uint8_t* dst = sA + s * A_GATHER_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            int iy = iy0[i] + ky, ix = ix0[i] + kx;
+            const bool ok = kvalid && iy >= 0 && iy < Hlog && ix >= 0 && ix < Wlog;
+            if (p.in_upsample) { iy >>= 1; ix >>= 1; }
+            const int64_t off = ((int64_t)(pixbase[i] + iy * p.Win + ix) * p.Cin + coff) * 2;
+            cp_async16(dst + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (it >= LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async_smem();
+            mbar_arrive(&a_full[(it - LAG) % SA]);
+          }
+        }
       }
-      cp_async_commit();
-      if (kb >= LAG) {
-        cp_async_wait<LAG>();
-        fence_proxy_async_smem();
-        mbar_arrive(&full_bar[(kb - LAG) % S]);
+    } else {
+      // HALO: 180 halo pixels x 8 chunks = 1440 pieces per 64-channel slab, 12 per thread
+      const int per_img = a.tiles_y * a.tiles_x;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles;
+        const int n = m_tile / per_img;
+        const int t = m_tile - n * per_img;
+        const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+        int32_t poff[12];   // element offset of the halo pixel (channel 0) or -1
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const int idx = tid + 128 * i;
+          const int pix = idx >> 3;
+          const int hy = pix / HALO_W, hx = pix - hy * HALO_W;
+          const int iy = ty * TILE_H - 1 + hy, ix = tx * TILE_W - 1 + hx;
+          const bool ok = pix < HALO_H * HALO_W && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+          poff[i] = ok ? ((n * p.Hin + iy) * p.Win + ix) * p.Cin : -1;
+        }
+        for (int slab = 0; slab < a.nslab; ++slab, ++it) {
+          const int s = it % SA;
+          mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1u);
+          uint8_t* dst = sA + s * A_HALO_BYTES;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) {
+            const int idx = tid + 128 * i;
+            const int pix = idx >> 3, chunk = idx & 7;
+            if (pix < HALO_H * HALO_W) {
+              const bool ok = poff[i] >= 0;
+              const int64_t off = ((int64_t)(ok ? poff[i] : 0) + slab * 64 + chunk * 8) * 2;
+              cp_async16(dst + pix * 128 + ((chunk ^ (pix & 7)) << 4), xbytes + (ok ? off : 0), ok ? 16u : 0u);
+            }
+          }
+          cp_async_commit();
+          if (it >= LAG) {
+            cp_async_wait<LAG>();
+            fence_proxy_async_smem();
+            mbar_arrive(&a_full[(it - LAG) % SA]);
+          }
+        }
       }
     }
-    // drain
-    if (KB >= 2) {
+    // drain the last (up to LAG) groups
+    if (it >= 2) {
       cp_async_wait<1>();
       fence_proxy_async_smem();
-      mbar_arrive(&full_bar[(KB - 2) % S]);
+      mbar_arrive(&a_full[(it - 2) % SA]);
     }
-    cp_async_wait<0>();
-    fence_proxy_async_smem();
-    mbar_arrive(&full_bar[(KB - 1) % S]);
-  } else {
-    if (warp == 4 && lane == 0) {
-      // =========================== B loader (TMA bulk) ======================
-      const uint8_t* wb = reinterpret_cast<const uint8_t*>(p.w) + (int64_t)n_tile * KB * C::kBStage;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], C::kBStage);
-        bulk_g2s(stage_base + s * C::kStageBytes + A_STAGE_BYTES, wb + (int64_t)kb * C::kBStage,
-                 C::kBStage, &full_bar[s]);
-      }
-    } else if (warp == 5 && lane == 0) {
-      // =========================== MMA issuer ===============================
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % S;
-        const uint32_t ph = (kb / S) & 1;
-        mbar_wait(&full_bar[s], ph);
-        tc_fence_after_sync();
-        const uint32_t sa = smem_u32(stage_base + s * C::kStageBytes);
-        const uint32_t sb = sa + A_STAGE_BYTES;
-#pragma unroll
-        for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-          const uint64_t da = make_smem_desc(sa + ks * 32, 16, 1024, LAYOUT_SW128);
-          const uint64_t db = make_smem_desc(sb + ks * 32, 16, 1024, LAYOUT_SW128);
-          umma_f16(tmem_base, da, db, a.idesc, (kb | ks) ? 1u : 0u);
-        }
-        umma_commit(&empty_bar[s]);
-      }
-      umma_commit(&tmem_full_bar);
+    if (it >= 1) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&a_full[(it - 1) % SA]);
     }
-    __syncwarp();
-    // =========================== epilogue (warps 4..7) ======================
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after_sync();
+  } else if (warp < 8) {
+    // ================================ epilogue ===========================================
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
-    const int64_t m = (int64_t)m_tile * BLOCK_M + row;
-    const bool row_ok = m < a.M;
     const int bf16 = p.dtype;
-    const int n_base = n_tile * BN;
-    const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16);
-    constexpr int G = (BN >= 32) ? 32 : 16;   // columns per TMEM load
+    constexpr int G = (BN >= 32) ? 32 : 16;
     constexpr int NG = BN / G;
-
-    float ln_shift = 0.f, ln_sum = 0.f, ln_sq = 0.f;
-    float mean = 0.f, rstd = 0.f;
-    const int passes = p.y_ln ? 2 : 1;
-    for (int pass = 0; pass < passes; ++pass) {
+    uint32_t acc_it = 0;
+    for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
+      const int m_tile = tile / a.n_tiles;
+      const int n_tile = tile - m_tile * a.n_tiles;
+      const int buf = acc_it & 1;
+      mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
+      tc_fence_after_sync();
+      const int64_t m = out_row_index(a, m_tile, row);
+      const bool row_ok = m >= 0;
+      const int n_base = n_tile * BN;
+      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * BN;
+      float ln_shift = 0.f, ln_sum = 0.f, ln_sq = 0.f, mean = 0.f, rstd = 0.f;
+      const int passes = p.y_ln ? 2 : 1;
+      for (int pass = 0; pass < passes; ++pass) {
 #pragma unroll 1
-      for (int g = 0; g < NG; ++g) {
-        uint32_t r[G];
-        if constexpr (G == 32) tmem_ld_32x32b_x32(trow + g * G, r);
-        else tmem_ld_32x32b_x16(trow + g * G, r);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        const int n0 = n_base + g * G;
-        float v[G];
+        for (int g = 0; g < NG; ++g) {
+          uint32_t r[G];
+          if constexpr (G == 32) tmem_ld_32x32b_x32(trow + g * G, r);
+          else tmem_ld_32x32b_x16(trow + g * G, r);
+          tmem_ld_wait();
+          if (!row_ok) continue;
+          const int n0 = n_base + g * G;
+          if (n0 >= p.Cout) continue;
+          float v[G];
 #pragma unroll
-        for (int j = 0; j < G; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias) {
+          for (int j = 0; j < G; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias) {
 #pragma unroll
-          for (int j = 0; j < G; ++j) if (n0 + j < p.Cout) v[j] += __ldg(p.bias + n0 + j);
-        }
-        const int64_t mr = p.res_rows > 0 ? (m % p.res_rows) : m;
-        if (p.res) {
-          const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
-#pragma unroll
-          for (int j = 0; j < G; j += 8) {
-            if (n0 + j + 8 <= p.Cout) {
-              const uint4 u = *reinterpret_cast<const uint4*>(rp + j * 2);
-              const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 f = unpack2(w4[t], bf16);
-                v[j + 2 * t] += f.x;
-                v[j + 2 * t + 1] += f.y;
-              }
-            }
+            for (int j = 0; j < G; ++j) if (n0 + j < p.Cout) v[j] += __ldg(p.bias + n0 + j);
           }
-        }
-        if (p.res32) {
-          const float* rp = p.res32 + mr * p.Cout + n0;
-#pragma unroll
-          for (int j = 0; j < G; j += 4) {
-            if (n0 + j + 4 <= p.Cout) {
-              const float4 f = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-            }
-          }
-        }
-        if (p.act == COBEVT_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < G; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (p.act == COBEVT_ACT_GELU) {
-#pragma unroll
-          for (int j = 0; j < G; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (pass == 0) {
-          if (p.y_ln) {
-            if (g == 0) ln_shift = v[0];
-#pragma unroll
-            for (int j = 0; j < G; ++j) {
-              const float d = v[j] - ln_shift;
-              ln_sum += d;
-              ln_sq += d * d;
-            }
-          }
-          if (p.y) {
-            uint8_t* yp = reinterpret_cast<uint8_t*>(p.y) + (m * p.Cout + n0) * 2;
+          const int64_t mr = p.res_rows > 0 ? (m % p.res_rows) : m;
+          if (p.res) {
+            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
 #pragma unroll
             for (int j = 0; j < G; j += 8) {
               if (n0 + j + 8 <= p.Cout) {
-                uint4 u;
-                u.x = pack2(v[j], v[j + 1], bf16);
-                u.y = pack2(v[j + 2], v[j + 3], bf16);
-                u.z = pack2(v[j + 4], v[j + 5], bf16);
-                u.w = pack2(v[j + 6], v[j + 7], bf16);
-                *reinterpret_cast<uint4*>(yp + j * 2) = u;
-              } else {
-                for (int t = 0; t < 8; ++t)
-                  if (n0 + j + t < p.Cout) {
-                    const uint32_t u = pack2(v[j + t], 0.f, bf16);
-                    *reinterpret_cast<uint16_t*>(yp + (j + t) * 2) = (uint16_t)(u & 0xFFFFu);
-                  }
+                const uint4 u = *reinterpret_cast<const uint4*>(rp + j * 2);
+                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                  const float2 f = unpack2(w4[t], bf16);
+                  v[j + 2 * t] += f.x;
+                  v[j + 2 * t + 1] += f.y;
+                }
               }
             }
           }
-          if (p.y32) {
-            float* yp = p.y32 + m * p.Cout + n0;
+          if (p.res32) {
+            const float* rp = p.res32 + mr * p.Cout + n0;
 #pragma unroll
             for (int j = 0; j < G; j += 4) {
               if (n0 + j + 4 <= p.Cout) {
-                *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              } else {
-                for (int t = 0; t < 4; ++t) if (n0 + j + t < p.Cout) yp[j + t] = v[j + t];
+                const float4 f = *reinterpret_cast<const float4*>(rp + j);
+                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
               }
             }
           }
-        } else {
-          uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
+          if (p.act == COBEVT_ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < G; ++j) v[j] = (v[j] - mean) * rstd;
-          if (p.ln_gamma) {
+            for (int j = 0; j < G; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act == COBEVT_ACT_GELU) {
 #pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = fmaf(v[j], __ldg(p.ln_gamma + n0 + j), __ldg(p.ln_beta + n0 + j));
+            for (int j = 0; j < G; ++j) v[j] = gelu_erf(v[j]);
           }
+          if (pass == 0) {
+            if (p.y_ln) {
+              if (g == 0) ln_shift = v[0];
 #pragma unroll
-          for (int j = 0; j < G; j += 8) {
-            uint4 u;
-            u.x = pack2(v[j], v[j + 1], bf16);
-            u.y = pack2(v[j + 2], v[j + 3], bf16);
-            u.z = pack2(v[j + 4], v[j + 5], bf16);
-            u.w = pack2(v[j + 6], v[j + 7], bf16);
-            *reinterpret_cast<uint4*>(yp + j * 2) = u;
+              for (int j = 0; j < G; ++j) {
+                const float d = v[j] - ln_shift;
+                ln_sum += d;
+                ln_sq += d * d;
+              }
+            }
+            if (p.y) {
+              uint8_t* yp = reinterpret_cast<uint8_t*>(p.y) + (m * p.Cout + n0) * 2;
+#pragma unroll
+              for (int j = 0; j < G; j += 8) {
+                if (n0 + j + 8 <= p.Cout) {
+                  uint4 u;
+                  u.x = pack2(v[j], v[j + 1], bf16);
+                  u.y = pack2(v[j + 2], v[j + 3], bf16);
+                  u.z = pack2(v[j + 4], v[j + 5], bf16);
+                  u.w = pack2(v[j + 6], v[j + 7], bf16);
+                  *reinterpret_cast<uint4*>(yp + j * 2) = u;
+                } else {
+                  for (int t = 0; t < 8; ++t)
+                    if (n0 + j + t < p.Cout) {
+                      const uint32_t u = pack2(v[j + t], 0.f, bf16);
+                      *reinterpret_cast<uint16_t*>(yp + (j + t) * 2) = (uint16_t)(u & 0xFFFFu);
+                    }
+                }
+              }
+            }
+            if (p.y32) {
+              float* yp = p.y32 + m * p.Cout + n0;
+#pragma unroll
+              for (int j = 0; j < G; j += 4) {
+                if (n0 + j + 4 <= p.Cout) {
+                  *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                } else {
+                  for (int t = 0; t < 4; ++t) if (n0 + j + t < p.Cout) yp[j + t] = v[j + t];
+                }
+              }
+            }
+          } else {
+            uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
+#pragma unroll
+            for (int j = 0; j < G; ++j) v[j] = (v[j] - mean) * rstd;
+            if (p.ln_gamma) {
+#pragma unroll
+              for (int j = 0; j < G; ++j) v[j] = fmaf(v[j], __ldg(p.ln_gamma + n0 + j), __ldg(p.ln_beta + n0 + j));
+            }
+#pragma unroll
+            for (int j = 0; j < G; j += 8) {
+              uint4 u;
+              u.x = pack2(v[j], v[j + 1], bf16);
+              u.y = pack2(v[j + 2], v[j + 3], bf16);
+              u.z = pack2(v[j + 4], v[j + 5], bf16);
+              u.w = pack2(v[j + 6], v[j + 7], bf16);
+              *reinterpret_cast<uint4*>(yp + j * 2) = u;
+            }
+          }
+        }
+        if (pass == 0 && p.y_ln) {
+          const float inv = 1.0f / (float)BN;
+          const float dm = ln_sum * inv;
+          mean = ln_shift + dm;
+          const float var = fmaxf(ln_sq * inv - dm * dm, 0.f);
+          rstd = rsqrtf(var + p.ln_eps);
+        }
+      }
+      // release the accumulator buffer
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
+    }
+  } else if (warp == 8) {
+    // ================================ B loader (TMA bulk) ================================
+    if (lane == 0) {
+      const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
+      if (a.resident_b) {
+        mbar_arrive_expect_tx(&b_res_full, (uint32_t)(KB * kBStage));
+        for (int kb = 0; kb < KB; ++kb) bulk_g2s(sB + kb * kBStage, wbase + (int64_t)kb * kBStage, kBStage, &b_res_full);
+      } else {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+          const int n_tile = tile % a.n_tiles;
+          const uint8_t* wb = wbase + (int64_t)n_tile * KB * kBStage;
+          for (int j = 0; j < KB; ++j, ++it) {
+            // consumption order: GATHER kb = j; HALO (slab-major, taps inner) kb = tap*nslab + slab
+            int kb = j;
+            if (a.mode == MODE_HALO) { const int slab = j / 9, tap = j - slab * 9; kb = tap * a.nslab + slab; }
+            const int s = it % SB;
+            mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1u);
+            mbar_arrive_expect_tx(&b_full[s], kBStage);
+            bulk_g2s(sB + s * kBStage, wb + (int64_t)kb * kBStage, kBStage, &b_full[s]);
           }
         }
       }
-      if (pass == 0 && p.y_ln) {
-        const float inv = 1.0f / (float)BN;
-        const float dm = ln_sum * inv;
-        mean = ln_shift + dm;
-        const float var = fmaxf(ln_sq * inv - dm * dm, 0.f);
-        rstd = rsqrtf(var + p.ln_eps);
+    }
+  } else if (warp == 9) {
+    // ================================ MMA issuer ==========================================
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      if (a.resident_b) mbar_wait(&b_res_full, 0);
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
+        const int buf = acc_it & 1;
+        mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1u);
+        tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + buf * BN;
+        uint32_t first = 1;
+        if (a.mode == MODE_GATHER) {
+          for (int kb = 0; kb < KB; ++kb, ++a_it) {
+            const int sa_ = a_it % SA;
+            mbar_wait(&a_full[sa_], (a_it / SA) & 1);
+            uint32_t sb_addr;
+            int sb_ = 0;
+            if (a.resident_b) {
+              sb_addr = smem_u32(sB + kb * kBStage);
+            } else {
+              sb_ = b_it % SB;
+              mbar_wait(&b_full[sb_], (b_it / SB) & 1);
+              sb_addr = smem_u32(sB + sb_ * kBStage);
+            }
+            tc_fence_after_sync();
+            const uint32_t sa_addr = smem_u32(sA + sa_ * A_GATHER_BYTES);
+#pragma unroll
+            for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
+              const uint64_t da = make_smem_desc(sa_addr + ks * 32, 16, 1024, LAYOUT_SW128);
+              const uint64_t db = make_smem_desc(sb_addr + ks * 32, 16, 1024, LAYOUT_SW128);
+              umma_f16(d_tmem, da, db, a.idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit(&a_empty[sa_]);
+            if (!a.resident_b) { umma_commit(&b_empty[sb_]); ++b_it; }
+          }
+        } else {
+          for (int slab = 0; slab < a.nslab; ++slab, ++a_it) {
+            const int sa_ = a_it % SA;
+            mbar_wait(&a_full[sa_], (a_it / SA) & 1);
+            const uint32_t sa_addr = smem_u32(sA + sa_ * A_HALO_BYTES);
+            for (int tap = 0; tap < 9; ++tap) {
+              uint32_t sb_addr;
+              int sb_ = 0;
+              if (a.resident_b) {
+                sb_addr = smem_u32(sB + (tap * a.nslab + slab) * kBStage);
+              } else {
+                sb_ = b_it % SB;
+                mbar_wait(&b_full[sb_], (b_it / SB) & 1);
+                sb_addr = smem_u32(sB + sb_ * kBStage);
+              }
+              tc_fence_after_sync();
+              const int ky = tap / 3, kx = tap - ky * 3;
+              const uint32_t a_tap = sa_addr + (ky * HALO_W + kx) * 128;
+#pragma unroll
+              for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
+                const uint64_t da = make_smem_desc(a_tap + ks * 32, 16, HALO_W * 128, LAYOUT_SW128);
+                const uint64_t db = make_smem_desc(sb_addr + ks * 32, 16, 1024, LAYOUT_SW128);
+                umma_f16(d_tmem, da, db, a.idesc, first ? 0u : 1u);
+                first = 0;
+              }
+              if (!a.resident_b) { umma_commit(&b_empty[sb_]); ++b_it; }
+            }
+            umma_commit(&a_empty[sa_]);
+          }
+        }
+        umma_commit(&acc_full[buf]);
       }
     }
   }
 
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+int g_num_sms = 0;
+
 template <int BN>
-int launch(const KArgs& a, cudaStream_t st) {
-  using C = Cfg<BN>;
-  const size_t smem = 1024 + (size_t)C::kStages * C::kStageBytes + BLOCK_M * sizeof(RowInfo) +
-                      (size_t)a.KB * 8 * sizeof(ChunkInfo);
-  if (smem > kMaxDynSmem) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: smem %zu too large (K=%d)", smem, a.K);
+int launch(KArgs& a, cudaStream_t st) {
+  constexpr int kBStage = BN * BLOCK_K * 2;
+  const int a_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
+  const int budget = kMaxDynSmem - 1024;
+  a.sa = a.mode == MODE_HALO ? 3 : 4;
+  const int64_t b_all = (int64_t)a.KB * kBStage;
+  a.resident_b = (a.n_tiles == 1 && b_all <= budget - a.sa * a_bytes && b_all < (1 << 20)) ? 1 : 0;
+  int64_t smem;
+  if (a.resident_b) {
+    a.sb = 1;
+    smem = 1024 + (int64_t)a.sa * a_bytes + b_all;
+  } else {
+    int sb = (budget - a.sa * a_bytes) / kBStage;
+    if (sb > MAX_STAGES) sb = MAX_STAGES;
+    if (sb < 2) { a.sa = 3; sb = (budget - a.sa * a_bytes) / kBStage; }   // SA must stay > LAG
+    if (sb < 2) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: no smem for the B ring (BN=%d)", BN);
+    a.sb = sb;
+    smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "conv: set smem attr: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  const int m_tiles = cobevt::ceil_div(a.M, BLOCK_M);
-  conv_gemm_kernel<BN><<<m_tiles * a.n_tiles, NUM_THREADS, smem, st>>>(a);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  conv_gemm_kernel<BN><<<grid, NUM_THREADS, (size_t)smem, st>>>(a);
   return cobevt::check_launch("conv_gemm_kernel");
 }
 
@@ -421,13 +560,28 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
   if (p->Cout % 8 != 0 && (p->res || p->y_ln)) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %% 8 with res/ln");
   const int64_t M64 = (int64_t)p->N * p->OH * p->OW;
   if (M64 > (1ll << 30)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: M too large");
+  if ((int64_t)p->N * p->Hin * p->Win * p->Cin >= (1ll << 31)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: input too large for 32-bit offsets");
   KArgs a;
+  memset(&a, 0, sizeof(a));
   a.p = *p;
   a.M = (int32_t)M64;
   a.K = p->KH * p->KW * p->Cin;
   a.KB = cobevt::ceil_div(a.K, BLOCK_K);
   a.n_tiles = cobevt::ceil_div(p->Cout, p->block_n);
   a.idesc = make_idesc_f16(128, p->block_n, p->dtype == COBEVT_BF16, false, false);
+  const bool halo = p->KH == 3 && p->KW == 3 && p->stride_h == 1 && p->stride_w == 1 && p->pad_h == 1 && p->pad_w == 1 &&
+                    p->Cin % 64 == 0 && !p->in_upsample && p->OH == p->Hin && p->OW == p->Win;
+  if (halo) {
+    a.mode = MODE_HALO;
+    a.tiles_y = cobevt::ceil_div(p->OH, TILE_H);
+    a.tiles_x = cobevt::ceil_div(p->OW, TILE_W);
+    a.nslab = p->Cin / 64;
+    a.m_tiles = p->N * a.tiles_y * a.tiles_x;
+  } else {
+    a.mode = MODE_GATHER;
+    a.m_tiles = cobevt::ceil_div(a.M, BLOCK_M);
+  }
+  a.total_tiles = a.m_tiles * a.n_tiles;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->block_n) {
     case 16: return launch<16>(a, st);

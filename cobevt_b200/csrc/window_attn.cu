@@ -323,6 +323,283 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
   if (warp == 0) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+
+// =====================================================================================
+// v2: one CTA per (batch row, window, head); the window's K/V (<= 1024 keys) are loaded ONCE
+// into shared memory and stay resident while two independent 128-thread warpgroups walk over
+// the query tiles / query views (ping-pong: one group's tcgen05 MMAs and TMEM traffic overlap
+// the other group's exp work).  Same math and operand layouts as the streaming kernel below.
+// =====================================================================================
+constexpr int KV_CAP_CHUNKS = 8;
+constexpr int V2_THREADS = 256;
+constexpr int V2_FIXED_SMEM = 1024 + 2 * SQ_BYTES + 2 * SP_BYTES;   // + n_chunks * (2*SK_BYTES + 512)
+
+__device__ __forceinline__ void wg_barrier(int wg) {
+  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+
+__global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_chunks = a.n_chunks;
+  uint8_t* sQ_all = smem;
+  uint8_t* sP_all = sQ_all + 2 * SQ_BYTES;
+  uint8_t* sK = sP_all + 2 * SP_BYTES;
+  uint8_t* sV = sK + n_chunks * SK_BYTES;
+  float* kmask = reinterpret_cast<float*>(sV + n_chunks * SK_BYTES);
+  __shared__ uint64_t bar_s[2], bar_o[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const CobevtAttnParams& p = a.p;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int wg = warp >> 2, wtid = tid & 127;
+  int item = blockIdx.x;
+  const int head = item % p.heads; item /= p.heads;
+  const int win = item % a.n_win;
+  const int b = item / a.n_win;
+  const int bf16 = p.dtype;
+
+  if (tid == 0) {
+    mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
+    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q);
+  const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
+  const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
+
+  // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all 256 threads ----------
+  for (int idx = tid; idx < n_chunks * CHUNK * 4; idx += V2_THREADS) {
+    const int tok = idx >> 2, piece = idx & 3;
+    const int c = tok >> 7, r = tok & 127;
+    const uint8_t* srcK = kb_;
+    const uint8_t* srcV = vb_;
+    uint32_t nb = 0;
+    float km = 0.f;
+    if (tok < a.Lk) {
+      const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, tok);
+      if (t.in_range) {
+        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kv_stride + head * DH;
+        srcK = kb_ + off * 2 + piece * 16;
+        srcV = vb_ + off * 2 + piece * 16;
+        nb = 16;
+        if (p.key_mask && piece == 0 &&
+            p.key_mask[(((int64_t)b * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kvmap.views + t.n] == 0)
+          km = -INFINITY;
+      } else if (p.k_pad) {
+        srcK = reinterpret_cast<const uint8_t*>(p.k_pad) + head * DH * 2 + piece * 16;
+        srcV = reinterpret_cast<const uint8_t*>(p.v_pad) + head * DH * 2 + piece * 16;
+        nb = 16;
+      }
+    } else {
+      km = -INFINITY;
+    }
+    cp_async16(sK + c * SK_BYTES + sw64_off(r, piece), srcK, nb);
+    cp_async16(sV + c * SK_BYTES + sw64_off(r, piece), srcV, nb);
+    if (piece == 0) kmask[tok] = km;
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s + wg * 256;
+  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  uint8_t* sQ = sQ_all + wg * SQ_BYTES;
+  uint8_t* sP = sP_all + wg * SP_BYTES;
+  uint64_t* bs = &bar_s[wg];
+  uint64_t* bo = &bar_o[wg];
+  uint32_t ph_s = 0, ph_o = 0;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
+  const bool any_mask = p.key_mask != nullptr;
+  const bool bias_vec = (a.Lk & 3) == 0;
+
+  for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
+    const int qrow = q_tile * TILE_Q + wtid;
+    const bool row_ok = qrow < rows_per_pass;
+    float acc[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+
+    for (int pass = 0; pass < a.q_passes; ++pass) {
+      // ---- Q tile: 4 lanes per row ----------------------------------------------------
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = wtid + 128 * i;
+        const int r = idx >> 2, piece = idx & 3;
+        const int rr = q_tile * TILE_Q + r;
+        const uint8_t* src = qb;
+        uint32_t nb = 0;
+        if (rr < rows_per_pass) {
+          const int t_idx = p.q_mean ? pass * rows_per_pass + rr : rr;
+          const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, t_idx);
+          const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
+          src = qb + off * 2 + piece * 16;
+          nb = 16;
+        }
+        cp_async16(sQ + sw64_off(r, piece), src, nb);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      wg_barrier(wg);
+
+      float m_run = -INFINITY, l_run = 0.f;
+      float o[DH];
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] = 0.f;
+
+      for (int c = 0; c < n_chunks; ++c) {
+        if (wtid == 0) {
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(sQ);
+          const uint32_t sb = smem_u32(sK + c * SK_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < DH / 16; ++ks) {
+            const uint64_t da = make_smem_desc(sa + ks * 32, 16, 512, LAYOUT_SW64);
+            const uint64_t db = make_smem_desc(sb + ks * 32, 16, 512, LAYOUT_SW64);
+            umma_f16(tmem_base, da, db, a.idesc_qk, ks ? 1u : 0u);
+          }
+          umma_commit(bs);
+        }
+        const int key0 = c * CHUNK;
+        const bool use_km = any_mask || (key0 + CHUNK > a.Lk);
+        mbar_wait(bs, ph_s);
+        ph_s ^= 1;
+        tc_fence_after_sync();
+
+        auto logits = [&](int g, float (&x)[32]) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + g * 32, r);
+          tmem_ld_wait();
+          const int kg = key0 + g * 32;
+          if (use_km) {
+            const float4* km4 = reinterpret_cast<const float4*>(kmask + kg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 k4 = km4[j];
+              x[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sl2, k4.x);
+              x[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sl2, k4.y);
+              x[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sl2, k4.z);
+              x[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sl2, k4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * sl2;
+          }
+          if (p.bias && row_ok) {
+            const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + kg;
+            if (bias_vec && kg + 32 <= a.Lk) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                x[4 * j + 0] = fmaf(b4.x, 1.4426950408889634f, x[4 * j + 0]);
+                x[4 * j + 1] = fmaf(b4.y, 1.4426950408889634f, x[4 * j + 1]);
+                x[4 * j + 2] = fmaf(b4.z, 1.4426950408889634f, x[4 * j + 2]);
+                x[4 * j + 3] = fmaf(b4.w, 1.4426950408889634f, x[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (kg + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
+            }
+          }
+        };
+        float mx = m_run;
+#pragma unroll 1
+        for (int g = 0; g < CHUNK / 32; ++g) {
+          float x[32];
+          logits(g, x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
+        }
+        const float m_safe = (mx == -INFINITY) ? 0.f : mx;
+        const float alpha = fast_exp2(m_run - m_safe);
+        float sum = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < CHUNK / 32; ++g) {
+          float x[32];
+          logits(g, x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            x[j] = fast_exp2(x[j] - m_safe);
+            sum += x[j];
+          }
+          uint8_t* dst = sP + (g >> 1) * (TILE_Q * 128);
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            uint4 u;
+            u.x = pack_h2(x[cc * 8 + 0], x[cc * 8 + 1], bf16);
+            u.y = pack_h2(x[cc * 8 + 2], x[cc * 8 + 3], bf16);
+            u.z = pack_h2(x[cc * 8 + 4], x[cc * 8 + 5], bf16);
+            u.w = pack_h2(x[cc * 8 + 6], x[cc * 8 + 7], bf16);
+            *reinterpret_cast<uint4*>(dst + sw128_off(wtid, (g & 1) * 4 + cc)) = u;
+          }
+        }
+        l_run = l_run * alpha + sum;
+        m_run = mx;
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+        wg_barrier(wg);
+        if (wtid == 0) {
+          tc_fence_after_sync();
+          const uint32_t sa = smem_u32(sP);
+          const uint32_t sv = smem_u32(sV + c * SK_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < CHUNK / 16; ++ks) {
+            const uint64_t da = make_smem_desc(sa + (ks >> 2) * (TILE_Q * 128) + (ks & 3) * 32, 16, 1024, LAYOUT_SW128);
+            const uint64_t db = make_smem_desc(sv + ks * 16 * 64, 512, 512, LAYOUT_SW64);
+            umma_f16(tmem_base + CHUNK, da, db, a.idesc_pv, ks ? 1u : 0u);
+          }
+          umma_commit(bo);
+        }
+        mbar_wait(bo, ph_o);
+        ph_o ^= 1;
+        tc_fence_after_sync();
+        {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_row + CHUNK, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(r[d]));
+        }
+        tc_fence_before_sync();
+      }
+      const float inv = (l_run > 0.f) ? 1.0f / (l_run * (float)a.q_passes) : 0.f;
+#pragma unroll
+      for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
+      wg_barrier(wg);   // sQ / sP are free again (all MMAs that read them have retired)
+    }
+
+    if (row_ok) {
+      const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
+      int64_t off;
+      if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+      else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+      uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint4 u;
+        u.x = pack_h2(acc[ch * 8 + 0], acc[ch * 8 + 1], bf16);
+        u.y = pack_h2(acc[ch * 8 + 2], acc[ch * 8 + 3], bf16);
+        u.z = pack_h2(acc[ch * 8 + 4], acc[ch * 8 + 5], bf16);
+        u.w = pack_h2(acc[ch * 8 + 6], acc[ch * 8 + 7], bf16);
+        *reinterpret_cast<uint4*>(op + ch * 16) = u;
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace
 
 extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
@@ -360,6 +637,18 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.idesc_pv = make_idesc_f16(128, DH, bf, false, true);
   const int64_t items = (int64_t)p->B * a.n_win * p->heads * a.q_tiles;
   if (items <= 0 || items > 0x7fffffff) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bad grid");
+  if (a.n_chunks <= KV_CAP_CHUNKS) {
+    const int smem = V2_FIXED_SMEM + a.n_chunks * (2 * SK_BYTES + CHUNK * 4);
+    static int attr_v2 = 0;
+    if (smem > attr_v2) {
+      cudaError_t e = cudaFuncSetAttribute(window_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
+      attr_v2 = smem;
+    }
+    const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
+    window_attn_v2_kernel<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    return cobevt::check_launch("window_attn_v2_kernel");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
