@@ -5,14 +5,17 @@
 // One CTA per SM walks over output tiles (128 rows x BN channels).  Warp roles:
 //   warps 0-3  A producers   16-byte cp.async (zero-fill outside the image) into K-major
 //                            SWIZZLE_128B stages; 8 lanes per 128-byte channel run (coalesced)
-//   warps 4-7  epilogue      one TMEM lane (= output row) per thread: +bias, +residual, ReLU /
-//                            GELU, optional row LayerNorm second output, 16-bit / fp32 stores;
-//                            the accumulator is double-buffered in TMEM so the epilogue of tile i
-//                            overlaps the main loop of tile i+1
-//   warp  8    B loader      weights pre-packed on the host as ready SWIZZLE_128B tile images,
+//   warps 4-11 epilogue      8 warps: TMEM lane quarter (warp % 4) x column half; one output row per
+//                            thread: all tcgen05.ld of the unit issued back to back, the accumulator
+//                            buffer is released as soon as it is in registers, then +bias (smem),
+//                            +residual (batched 16-byte loads), ReLU / GELU, optional row LayerNorm
+//                            second output (the two column halves exchange mean / M2 through smem),
+//                            16-bit / fp32 stores.  The accumulator is double-buffered in TMEM so
+//                            tile i's epilogue overlaps tile i+1's main loop
+//   warp  12   B loader      weights pre-packed on the host as ready SWIZZLE_128B tile images,
 //                            one cp.async.bulk (TMA engine) per k-block, or ALL k-blocks once when
 //                            they fit (resident weights: token GEMMs and 64-channel convs)
-//   warp  9    MMA issuer    one thread, tcgen05.mma M=128 N=BN K=16; tcgen05.commit frees stages
+//   warp  13   MMA issuer    one thread, tcgen05.mma M=128 N=BN K=16; tcgen05.commit frees stages
 //
 // A-operand modes
 //   GATHER  any conv: per 64-wide k-block the 128 x 64 im2col slice is gathered from the NHWC
@@ -40,8 +43,9 @@ constexpr int BLOCK_K = 64;
 constexpr int A_GATHER_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
 constexpr int A_HALO_BYTES = 24 * 1024;                // 180 rows x 128 B = 23040, padded to 1 KB multiple
-constexpr int NUM_THREADS = 320;
-constexpr int kMaxDynSmem = 227 * 1024 - 2048;         // static smem (barriers) counts against 227 KB
+constexpr int NUM_THREADS = 448;
+constexpr int LAG_GATHER = 4, LAG_HALO = 2;
+constexpr int kMaxDynSmem = 227 * 1024 - 8192;         // static smem (barriers, bias, LN exchange) counts too
 constexpr int MAX_STAGES = 8;
 
 enum { MODE_GATHER = 0, MODE_HALO = 1 };
@@ -86,10 +90,29 @@ __device__ __forceinline__ int64_t out_row_index(const KArgs& a, int m_tile, int
   return m < a.M ? m : -1;
 }
 
+// one epilogue unit: U accumulator columns of this thread's row
+template <int U>
+__device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&r)[U]) {
+  if constexpr (U == 16) {
+    tmem_ld_32x32b_x16(taddr, r);
+  } else {
+#pragma unroll
+    for (int g = 0; g < U / 32; ++g) {
+      uint32_t t[32];
+      tmem_ld_32x32b_x32(taddr + g * 32, t);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[g * 32 + j] = t[j];
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a) {
   constexpr int kBStage = BN * BLOCK_K * 2;
   constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
+  constexpr int CW = BN >= 64 ? BN / 2 : BN;      // columns per epilogue warp
+  constexpr int U = CW > 64 ? 64 : CW;            // columns per unit
+  constexpr int NU = CW / U;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int SA = a.sa, SB = a.sb;
@@ -99,6 +122,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
   __shared__ uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES];
   __shared__ uint64_t acc_full[2], acc_empty[2], b_res_full;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float sBias[512], sGamma[128], sBeta[128];
+  __shared__ float2 sXch[2][2][128];              // [tile parity][column half][row] = (mean, M2)
 
   const CobevtConvParams& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,13 +137,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
       mbar_init(&b_empty[s], 1);
     }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 4); mbar_init(&acc_empty[1], 4);
+    mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
     mbar_init(&b_res_full, 1);
     mbar_fence_init();
   }
   if (warp == 4) {
     tmem_alloc(&tmem_base_s, kTmemCols);
     tmem_relinquish();
+  }
+  for (int i = tid; i < 512; i += NUM_THREADS) sBias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
+  if (tid < 128) {
+    sGamma[tid] = p.ln_gamma ? p.ln_gamma[tid] : 1.f;
+    sBeta[tid] = p.ln_beta ? p.ln_beta[tid] : 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -129,8 +159,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
     // ================================ A producers ========================================
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
     uint32_t it = 0;   // stage uses issued so far (across tiles)
-    constexpr int LAG = 2;
     if (a.mode == MODE_GATHER) {
+      constexpr int LAG = LAG_GATHER;
       const int Hlog = p.in_upsample ? p.Hin * 2 : p.Hin;
       const int Wlog = p.in_upsample ? p.Win * 2 : p.Win;
       const int c8 = tid & 7, r0 = tid >> 3;
@@ -178,8 +208,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
           }
         }
       }
+      // drain the last (up to LAG) groups
+      if (it >= 4) { cp_async_wait<3>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 4) % SA]); }
+      if (it >= 3) { cp_async_wait<2>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 3) % SA]); }
+      if (it >= 2) { cp_async_wait<1>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 2) % SA]); }
+      if (it >= 1) { cp_async_wait<0>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 1) % SA]); }
     } else {
       // HALO: 180 halo pixels x 8 chunks = 1440 pieces per 64-channel slab, 12 per thread
+      constexpr int LAG = LAG_HALO;
       const int per_img = a.tiles_y * a.tiles_x;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int m_tile = tile / a.n_tiles;
@@ -218,25 +254,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
           }
         }
       }
+      if (it >= 2) { cp_async_wait<1>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 2) % SA]); }
+      if (it >= 1) { cp_async_wait<0>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 1) % SA]); }
     }
-    // drain the last (up to LAG) groups
-    if (it >= 2) {
-      cp_async_wait<1>();
-      fence_proxy_async_smem();
-      mbar_arrive(&a_full[(it - 2) % SA]);
-    }
-    if (it >= 1) {
-      cp_async_wait<0>();
-      fence_proxy_async_smem();
-      mbar_arrive(&a_full[(it - 1) % SA]);
-    }
-  } else if (warp < 8) {
-    // ================================ epilogue ===========================================
-    const int q4 = warp & 3;
+  } else if (warp < 12) {
+    // ================================ epilogue (8 warps) =================================
+    const int e = warp - 4;
+    const int q4 = e & 3;             // TMEM lane quarter (== warp % 4)
+    const int hf = e >> 2;            // column half
+    const bool active = (BN >= 64) || (hf == 0);
     const int row = q4 * 32 + lane;
     const int bf16 = p.dtype;
-    constexpr int G = (BN >= 32) ? 32 : 16;
-    constexpr int NG = BN / G;
+    const bool do_ln = p.y_ln != nullptr;      // host guarantees BN == Cout == 128 -> CW == U == 64
     uint32_t acc_it = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
       const int m_tile = tile / a.n_tiles;
@@ -244,137 +273,139 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
       const int buf = acc_it & 1;
       mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
       tc_fence_after_sync();
+      if (!active) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
       const int64_t m = out_row_index(a, m_tile, row);
       const bool row_ok = m >= 0;
-      const int n_base = n_tile * BN;
-      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * BN;
-      float ln_shift = 0.f, ln_sum = 0.f, ln_sq = 0.f, mean = 0.f, rstd = 0.f;
-      const int passes = p.y_ln ? 2 : 1;
-      for (int pass = 0; pass < passes; ++pass) {
+      const int64_t mr = p.res_rows > 0 ? ((row_ok ? m : 0) % p.res_rows) : m;
+      const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * BN + hf * CW;
 #pragma unroll 1
-        for (int g = 0; g < NG; ++g) {
-          uint32_t r[G];
-          if constexpr (G == 32) tmem_ld_32x32b_x32(trow + g * G, r);
-          else tmem_ld_32x32b_x16(trow + g * G, r);
-          tmem_ld_wait();
-          if (!row_ok) continue;
-          const int n0 = n_base + g * G;
-          if (n0 >= p.Cout) continue;
-          float v[G];
+      for (int u = 0; u < NU; ++u) {
+        const int col = hf * CW + u * U;           // column inside the tile
+        const int n0 = n_tile * BN + col;          // global output channel
+        uint32_t r[U];
+        tmem_ld_unit<U>(trow + u * U, r);
+        tmem_ld_wait();
+        if (u == NU - 1) {                         // accumulator is in registers: hand the buffer back
+          tc_fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        }
+        const bool live = row_ok && n0 < p.Cout;
+        float v[U];
 #pragma unroll
-          for (int j = 0; j < G; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias) {
+        for (int j = 0; j < U; ++j) v[j] = __uint_as_float(r[j]) + sBias[(n0 + j) & 511];
+        if (live && p.res) {
+          const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
 #pragma unroll
-            for (int j = 0; j < G; ++j) if (n0 + j < p.Cout) v[j] += __ldg(p.bias + n0 + j);
-          }
-          const int64_t mr = p.res_rows > 0 ? (m % p.res_rows) : m;
-          if (p.res) {
-            const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
+          for (int j0 = 0; j0 < U; j0 += 32) {
+            uint4 rr[4];
 #pragma unroll
-            for (int j = 0; j < G; j += 8) {
-              if (n0 + j + 8 <= p.Cout) {
-                const uint4 u = *reinterpret_cast<const uint4*>(rp + j * 2);
-                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+            for (int t = 0; t < 4; ++t)
+              rr[t] = (j0 + t * 8 < U && n0 + j0 + t * 8 + 8 <= p.Cout)
+                          ? *reinterpret_cast<const uint4*>(rp + (j0 + t * 8) * 2) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int t = 0; t < 4; ++t) {
-                  const float2 f = unpack2(w4[t], bf16);
-                  v[j + 2 * t] += f.x;
-                  v[j + 2 * t + 1] += f.y;
+            for (int t = 0; t < 4; ++t) {
+              if (j0 + t * 8 < U) {
+                const uint32_t w4[4] = {rr[t].x, rr[t].y, rr[t].z, rr[t].w};
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                  const float2 f = unpack2(w4[k2], bf16);
+                  v[j0 + t * 8 + 2 * k2] += f.x;
+                  v[j0 + t * 8 + 2 * k2 + 1] += f.y;
                 }
               }
-            }
-          }
-          if (p.res32) {
-            const float* rp = p.res32 + mr * p.Cout + n0;
-#pragma unroll
-            for (int j = 0; j < G; j += 4) {
-              if (n0 + j + 4 <= p.Cout) {
-                const float4 f = *reinterpret_cast<const float4*>(rp + j);
-                v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
-              }
-            }
-          }
-          if (p.act == COBEVT_ACT_RELU) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act == COBEVT_ACT_GELU) {
-#pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if (pass == 0) {
-            if (p.y_ln) {
-              if (g == 0) ln_shift = v[0];
-#pragma unroll
-              for (int j = 0; j < G; ++j) {
-                const float d = v[j] - ln_shift;
-                ln_sum += d;
-                ln_sq += d * d;
-              }
-            }
-            if (p.y) {
-              uint8_t* yp = reinterpret_cast<uint8_t*>(p.y) + (m * p.Cout + n0) * 2;
-#pragma unroll
-              for (int j = 0; j < G; j += 8) {
-                if (n0 + j + 8 <= p.Cout) {
-                  uint4 u;
-                  u.x = pack2(v[j], v[j + 1], bf16);
-                  u.y = pack2(v[j + 2], v[j + 3], bf16);
-                  u.z = pack2(v[j + 4], v[j + 5], bf16);
-                  u.w = pack2(v[j + 6], v[j + 7], bf16);
-                  *reinterpret_cast<uint4*>(yp + j * 2) = u;
-                } else {
-                  for (int t = 0; t < 8; ++t)
-                    if (n0 + j + t < p.Cout) {
-                      const uint32_t u = pack2(v[j + t], 0.f, bf16);
-                      *reinterpret_cast<uint16_t*>(yp + (j + t) * 2) = (uint16_t)(u & 0xFFFFu);
-                    }
-                }
-              }
-            }
-            if (p.y32) {
-              float* yp = p.y32 + m * p.Cout + n0;
-#pragma unroll
-              for (int j = 0; j < G; j += 4) {
-                if (n0 + j + 4 <= p.Cout) {
-                  *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                } else {
-                  for (int t = 0; t < 4; ++t) if (n0 + j + t < p.Cout) yp[j + t] = v[j + t];
-                }
-              }
-            }
-          } else {
-            uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
-#pragma unroll
-            for (int j = 0; j < G; ++j) v[j] = (v[j] - mean) * rstd;
-            if (p.ln_gamma) {
-#pragma unroll
-              for (int j = 0; j < G; ++j) v[j] = fmaf(v[j], __ldg(p.ln_gamma + n0 + j), __ldg(p.ln_beta + n0 + j));
-            }
-#pragma unroll
-            for (int j = 0; j < G; j += 8) {
-              uint4 u;
-              u.x = pack2(v[j], v[j + 1], bf16);
-              u.y = pack2(v[j + 2], v[j + 3], bf16);
-              u.z = pack2(v[j + 4], v[j + 5], bf16);
-              u.w = pack2(v[j + 6], v[j + 7], bf16);
-              *reinterpret_cast<uint4*>(yp + j * 2) = u;
             }
           }
         }
-        if (pass == 0 && p.y_ln) {
-          const float inv = 1.0f / (float)BN;
-          const float dm = ln_sum * inv;
-          mean = ln_shift + dm;
-          const float var = fmaxf(ln_sq * inv - dm * dm, 0.f);
-          rstd = rsqrtf(var + p.ln_eps);
+        if (live && p.res32) {
+          const float* rp = p.res32 + mr * p.Cout + n0;
+#pragma unroll
+          for (int j = 0; j < U; j += 4) {
+            if (n0 + j + 4 <= p.Cout) {
+              const float4 f = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += f.x; v[j + 1] += f.y; v[j + 2] += f.z; v[j + 3] += f.w;
+            }
+          }
+        }
+        if (p.act == COBEVT_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act == COBEVT_ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < U; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (live && p.y) {
+          uint8_t* yp = reinterpret_cast<uint8_t*>(p.y) + (m * p.Cout + n0) * 2;
+#pragma unroll
+          for (int j = 0; j < U; j += 8) {
+            if (n0 + j + 8 <= p.Cout) {
+              uint4 w;
+              w.x = pack2(v[j], v[j + 1], bf16);
+              w.y = pack2(v[j + 2], v[j + 3], bf16);
+              w.z = pack2(v[j + 4], v[j + 5], bf16);
+              w.w = pack2(v[j + 6], v[j + 7], bf16);
+              *reinterpret_cast<uint4*>(yp + j * 2) = w;
+            } else {
+              for (int t = 0; t < 8; ++t)
+                if (n0 + j + t < p.Cout) {
+                  const uint32_t w = pack2(v[j + t], 0.f, bf16);
+                  *reinterpret_cast<uint16_t*>(yp + (j + t) * 2) = (uint16_t)(w & 0xFFFFu);
+                }
+            }
+          }
+        }
+        if (live && p.y32) {
+          float* yp = p.y32 + m * p.Cout + n0;
+#pragma unroll
+          for (int j = 0; j < U; j += 4) {
+            if (n0 + j + 4 <= p.Cout) {
+              *reinterpret_cast<float4*>(yp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+              for (int t = 0; t < 4; ++t) if (n0 + j + t < p.Cout) yp[j + t] = v[j + t];
+            }
+          }
+        }
+        if constexpr (BN == 128) {
+          if (do_ln) {
+            // exact two-pass statistics on this half (64 values in registers), then combine the halves
+            float s1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < U; ++j) s1 += v[j];
+            const float mh = s1 * (1.0f / U);
+            float m2 = 0.f;
+#pragma unroll
+            for (int j = 0; j < U; ++j) { const float d = v[j] - mh; m2 += d * d; }
+            const int par = acc_it & 1;
+            sXch[par][hf][row] = make_float2(mh, m2);
+            asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory");
+            const float2 o = sXch[par][hf ^ 1][row];
+            const float mean = 0.5f * (mh + o.x);
+            const float dlt = mh - o.x;
+            const float var = (m2 + o.y + dlt * dlt * (float)(U / 2)) * (1.0f / (2 * U));
+            const float rstd = rsqrtf(var + p.ln_eps);
+            if (live) {
+              uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
+#pragma unroll
+              for (int j = 0; j < U; ++j) v[j] = fmaf((v[j] - mean) * rstd, sGamma[(col + j) & 127], sBeta[(col + j) & 127]);
+#pragma unroll
+              for (int j = 0; j < U; j += 8) {
+                uint4 w;
+                w.x = pack2(v[j], v[j + 1], bf16);
+                w.y = pack2(v[j + 2], v[j + 3], bf16);
+                w.z = pack2(v[j + 4], v[j + 5], bf16);
+                w.w = pack2(v[j + 6], v[j + 7], bf16);
+                *reinterpret_cast<uint4*>(yp + j * 2) = w;
+              }
+            }
+          }
         }
       }
-      // release the accumulator buffer
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
-  } else if (warp == 8) {
+  } else if (warp == 12) {
     // ================================ B loader (TMA bulk) ================================
     if (lane == 0) {
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
@@ -398,10 +429,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == 13) {
     // ================================ MMA issuer ==========================================
     if (lane == 0) {
       uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      // descriptor templates: only the 14-bit start-address field changes per MMA
+      const uint64_t dA_gather = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const uint64_t dA_halo = make_smem_desc(0, 16, HALO_W * 128, LAYOUT_SW128);
+      const uint64_t dB = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       if (a.resident_b) mbar_wait(&b_res_full, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
         const int buf = acc_it & 1;
@@ -426,9 +461,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             const uint32_t sa_addr = smem_u32(sA + sa_ * A_GATHER_BYTES);
 #pragma unroll
             for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-              const uint64_t da = make_smem_desc(sa_addr + ks * 32, 16, 1024, LAYOUT_SW128);
-              const uint64_t db = make_smem_desc(sb_addr + ks * 32, 16, 1024, LAYOUT_SW128);
-              umma_f16(d_tmem, da, db, a.idesc, first ? 0u : 1u);
+              umma_f16(d_tmem, dA_gather | (uint64_t)(((sa_addr + ks * 32) >> 4) & 0x3FFF),
+                       dB | (uint64_t)(((sb_addr + ks * 32) >> 4) & 0x3FFF), a.idesc, first ? 0u : 1u);
               first = 0;
             }
             umma_commit(&a_empty[sa_]);
@@ -454,9 +488,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
               const uint32_t a_tap = sa_addr + (ky * HALO_W + kx) * 128;
 #pragma unroll
               for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-                const uint64_t da = make_smem_desc(a_tap + ks * 32, 16, HALO_W * 128, LAYOUT_SW128);
-                const uint64_t db = make_smem_desc(sb_addr + ks * 32, 16, 1024, LAYOUT_SW128);
-                umma_f16(d_tmem, da, db, a.idesc, first ? 0u : 1u);
+                umma_f16(d_tmem, dA_halo | (uint64_t)(((a_tap + ks * 32) >> 4) & 0x3FFF),
+                         dB | (uint64_t)(((sb_addr + ks * 32) >> 4) & 0x3FFF), a.idesc, first ? 0u : 1u);
                 first = 0;
               }
               if (!a.resident_b) { umma_commit(&b_empty[sb_]); ++b_it; }
@@ -481,7 +514,7 @@ int launch(KArgs& a, cudaStream_t st) {
   constexpr int kBStage = BN * BLOCK_K * 2;
   const int a_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
   const int budget = kMaxDynSmem - 1024;
-  a.sa = a.mode == MODE_HALO ? 3 : 4;
+  a.sa = a.mode == MODE_HALO ? LAG_HALO + 2 : LAG_GATHER + 2;   // SA > LAG + 1: producers never wait on the MMA
   const int64_t b_all = (int64_t)a.KB * kBStage;
   a.resident_b = (a.n_tiles == 1 && b_all <= budget - a.sa * a_bytes && b_all < (1 << 20)) ? 1 : 0;
   int64_t smem;
@@ -491,7 +524,7 @@ int launch(KArgs& a, cudaStream_t st) {
   } else {
     int sb = (budget - a.sa * a_bytes) / kBStage;
     if (sb > MAX_STAGES) sb = MAX_STAGES;
-    if (sb < 2) { a.sa = 3; sb = (budget - a.sa * a_bytes) / kBStage; }   // SA must stay > LAG
+    if (sb < 2) { a.sa = (a.mode == MODE_HALO ? LAG_HALO : LAG_GATHER) + 1; sb = (budget - a.sa * a_bytes) / kBStage; }
     if (sb < 2) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: no smem for the B ring (BN=%d)", BN);
     a.sb = sb;
     smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
@@ -557,6 +590,7 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
   if (p->y_ln && !(p->Cout == 128 && p->block_n == 128))
     return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: y_ln needs Cout == block_n == 128");
   if ((p->ln_gamma == nullptr) != (p->ln_beta == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: ln_gamma/ln_beta must come together");
+  if (p->Cout > 512) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %d > 512", p->Cout);
   if (p->Cout % 8 != 0 && (p->res || p->y_ln)) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %% 8 with res/ln");
   const int64_t M64 = (int64_t)p->N * p->OH * p->OW;
   if (M64 > (1ll << 30)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: M too large");

@@ -325,14 +325,20 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
 
 
 // =====================================================================================
-// v2: one CTA per (batch row, window, head); the window's K/V (<= 1024 keys) are loaded ONCE
-// into shared memory and stay resident while two independent 128-thread warpgroups walk over
-// the query tiles / query views (ping-pong: one group's tcgen05 MMAs and TMEM traffic overlap
-// the other group's exp work).  Same math and operand layouts as the streaming kernel below.
+// Resident-KV kernel: one CTA per (batch row, window, head).  The window's K/V (<= 1024 keys) are
+// loaded ONCE into shared memory; two independent 128-thread warpgroups walk over the 128-row
+// query tiles / query views.  Inside a warpgroup the tensor-core work is software-pipelined over
+// 64-key chunks so no MMA latency sits on the exp critical path:
+//     iteration c:  issue S(c+1)=Q K(c+1)^T  |  softmax of S(c) (held in 64 registers)  |
+//                   issue O(c)=P(c) V(c)     |  fold the finished O(c-1) into the running output
+// S and O are double-buffered in TMEM (2x64 + 2x32 columns per warpgroup), P in shared memory.
+// Same operand layouts as the streaming kernel above (V used as an MN-major B operand).
 // =====================================================================================
-constexpr int KV_CAP_CHUNKS = 8;
+constexpr int CH = 64;                                 // keys per chunk
+constexpr int KV_CAP_KEYS = 1024;
 constexpr int V2_THREADS = 256;
-constexpr int V2_FIXED_SMEM = 1024 + 2 * SQ_BYTES + 2 * SP_BYTES;   // + n_chunks * (2*SK_BYTES + 512)
+constexpr int SP2_BYTES = TILE_Q * CH * 2;             // 16 KB per P buffer
+constexpr int V2_FIXED_SMEM = 1024 + 2 * SQ_BYTES + 2 * 2 * SP2_BYTES;   // + keys * (128 B K/V + 4 B mask)
 
 __device__ __forceinline__ void wg_barrier(int wg) {
   asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
@@ -341,13 +347,14 @@ __device__ __forceinline__ void wg_barrier(int wg) {
 __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int n_chunks = a.n_chunks;
+  const int n_ch = (a.Lk + CH - 1) / CH;
+  const int keys_pad = n_ch * CH;
   uint8_t* sQ_all = smem;
   uint8_t* sP_all = sQ_all + 2 * SQ_BYTES;
-  uint8_t* sK = sP_all + 2 * SP_BYTES;
-  uint8_t* sV = sK + n_chunks * SK_BYTES;
-  float* kmask = reinterpret_cast<float*>(sV + n_chunks * SK_BYTES);
-  __shared__ uint64_t bar_s[2], bar_o[2];
+  uint8_t* sK = sP_all + 4 * SP2_BYTES;
+  uint8_t* sV = sK + keys_pad * 64;
+  float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
+  __shared__ uint64_t bar_s[2][2], bar_o[2][2];
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
@@ -360,8 +367,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   const int bf16 = p.dtype;
 
   if (tid == 0) {
-    mbar_init(&bar_s[0], 1); mbar_init(&bar_s[1], 1);
-    mbar_init(&bar_o[0], 1); mbar_init(&bar_o[1], 1);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) { mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -373,9 +382,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
 
   // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all 256 threads ----------
-  for (int idx = tid; idx < n_chunks * CHUNK * 4; idx += V2_THREADS) {
+  for (int idx = tid; idx < keys_pad * 4; idx += V2_THREADS) {
     const int tok = idx >> 2, piece = idx & 3;
-    const int c = tok >> 7, r = tok & 127;
     const uint8_t* srcK = kb_;
     const uint8_t* srcV = vb_;
     uint32_t nb = 0;
@@ -398,8 +406,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     } else {
       km = -INFINITY;
     }
-    cp_async16(sK + c * SK_BYTES + sw64_off(r, piece), srcK, nb);
-    cp_async16(sV + c * SK_BYTES + sw64_off(r, piece), srcV, nb);
+    cp_async16(sK + sw64_off(tok, piece), srcK, nb);
+    cp_async16(sV + sw64_off(tok, piece), srcV, nb);
     if (piece == 0) kmask[tok] = km;
   }
   cp_async_commit();
@@ -408,17 +416,36 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_s + wg * 256;
+  const uint32_t tmem_base = tmem_base_s + wg * 256;   // S0 [0,64) S1 [64,128) O0 [128,160) O1 [160,192)
   const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sQ = sQ_all + wg * SQ_BYTES;
-  uint8_t* sP = sP_all + wg * SP_BYTES;
-  uint64_t* bs = &bar_s[wg];
-  uint64_t* bo = &bar_o[wg];
-  uint32_t ph_s = 0, ph_o = 0;
+  uint8_t* sP = sP_all + wg * 2 * SP2_BYTES;
+  uint32_t ph_s[2] = {0, 0}, ph_o[2] = {0, 0};
   const float sl2 = p.scale * 1.4426950408889634f;
   const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
   const bool any_mask = p.key_mask != nullptr;
   const bool bias_vec = (a.Lk & 3) == 0;
+  const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
+  const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+  const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);
+  auto desc_at = [](uint64_t d, uint32_t addr) { return d | (uint64_t)((addr >> 4) & 0x3FFF); };
+
+  auto issue_qk = [&](int c) {       // S(c) = Q K(c)^T  -> S buffer c&1
+    tc_fence_after_sync();
+    const uint32_t sa = smem_u32(sQ), sb = smem_u32(sK + c * CH * 64);
+#pragma unroll
+    for (int ks = 0; ks < DH / 16; ++ks)
+      umma_f16(tmem_base + (c & 1) * CH, desc_at(dQK, sa + ks * 32), desc_at(dQK, sb + ks * 32), a.idesc_qk, ks ? 1u : 0u);
+    umma_commit(&bar_s[wg][c & 1]);
+  };
+  auto issue_pv = [&](int c) {       // O(c) = P(c) V(c)  -> O buffer c&1
+    tc_fence_after_sync();
+    const uint32_t sa = smem_u32(sP + (c & 1) * SP2_BYTES), sv = smem_u32(sV + c * CH * 64);
+#pragma unroll
+    for (int ks = 0; ks < CH / 16; ++ks)
+      umma_f16(tmem_base + 2 * CH + (c & 1) * DH, desc_at(dP, sa + ks * 32), desc_at(dV, sv + ks * 16 * 64), a.idesc_pv, ks ? 1u : 0u);
+    umma_commit(&bar_o[wg][c & 1]);
+  };
 
   for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
     const int qrow = q_tile * TILE_Q + wtid;
@@ -450,55 +477,58 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       fence_proxy_async_smem();
       tc_fence_before_sync();
       wg_barrier(wg);
+      if (wtid == 0) issue_qk(0);
 
-      float m_run = -INFINITY, l_run = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
       float o[DH];
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] = 0.f;
 
-      for (int c = 0; c < n_chunks; ++c) {
-        if (wtid == 0) {
-          tc_fence_after_sync();
-          const uint32_t sa = smem_u32(sQ);
-          const uint32_t sb = smem_u32(sK + c * SK_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < DH / 16; ++ks) {
-            const uint64_t da = make_smem_desc(sa + ks * 32, 16, 512, LAYOUT_SW64);
-            const uint64_t db = make_smem_desc(sb + ks * 32, 16, 512, LAYOUT_SW64);
-            umma_f16(tmem_base, da, db, a.idesc_qk, ks ? 1u : 0u);
-          }
-          umma_commit(bs);
-        }
-        const int key0 = c * CHUNK;
-        const bool use_km = any_mask || (key0 + CHUNK > a.Lk);
-        mbar_wait(bs, ph_s);
-        ph_s ^= 1;
+      for (int c = 0; c < n_ch; ++c) {
+        const int sb = c & 1;
+        if (wtid == 0 && c + 1 < n_ch) issue_qk(c + 1);
+        const int key0 = c * CH;
+        const bool use_km = any_mask || (key0 + CH > a.Lk);
+        mbar_wait(&bar_s[wg][sb], ph_s[sb]);
+        ph_s[sb] ^= 1;
         tc_fence_after_sync();
-
-        auto logits = [&](int g, float (&x)[32]) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + g * 32, r);
+        // ---- logits of this row: 64 registers ------------------------------------------
+        float x[CH];
+        {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32b_x32(t_row + sb * CH, r0);
+          tmem_ld_32x32b_x32(t_row + sb * CH + 32, r1);
           tmem_ld_wait();
-          const int kg = key0 + g * 32;
-          if (use_km) {
-            const float4* km4 = reinterpret_cast<const float4*>(kmask + kg);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(r0[j]); x[32 + j] = __uint_as_float(r1[j]); }
+        }
+        float mx;
+        const bool plain = !use_km && !(p.bias != nullptr);
+        if (plain) {
+          float mr = x[0];
+#pragma unroll
+          for (int j = 1; j < CH; ++j) mr = fmaxf(mr, x[j]);
+          mx = fmaxf(m_run, mr * sl2);
+        } else {
+          if (use_km) {
+            const float4* km4 = reinterpret_cast<const float4*>(kmask + key0);
+#pragma unroll
+            for (int j = 0; j < CH / 4; ++j) {
               const float4 k4 = km4[j];
-              x[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sl2, k4.x);
-              x[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sl2, k4.y);
-              x[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sl2, k4.z);
-              x[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sl2, k4.w);
+              x[4 * j + 0] = fmaf(x[4 * j + 0], sl2, k4.x);
+              x[4 * j + 1] = fmaf(x[4 * j + 1], sl2, k4.y);
+              x[4 * j + 2] = fmaf(x[4 * j + 2], sl2, k4.z);
+              x[4 * j + 3] = fmaf(x[4 * j + 3], sl2, k4.w);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]) * sl2;
+            for (int j = 0; j < CH; ++j) x[j] *= sl2;
           }
           if (p.bias && row_ok) {
-            const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + kg;
-            if (bias_vec && kg + 32 <= a.Lk) {
+            const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
+            if (bias_vec && key0 + CH <= a.Lk) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < CH / 4; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
                 x[4 * j + 0] = fmaf(b4.x, 1.4426950408889634f, x[4 * j + 0]);
                 x[4 * j + 1] = fmaf(b4.y, 1.4426950408889634f, x[4 * j + 1]);
@@ -507,75 +537,74 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (kg + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
+              for (int j = 0; j < CH; ++j)
+                if (key0 + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
             }
           }
-        };
-        float mx = m_run;
-#pragma unroll 1
-        for (int g = 0; g < CHUNK / 32; ++g) {
-          float x[32];
-          logits(g, x);
+          mx = m_run;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, x[j]);
+          for (int j = 0; j < CH; ++j) mx = fmaxf(mx, x[j]);
         }
         const float m_safe = (mx == -INFINITY) ? 0.f : mx;
         const float alpha = fast_exp2(m_run - m_safe);
         float sum = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < CHUNK / 32; ++g) {
-          float x[32];
-          logits(g, x);
+        if (plain) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            x[j] = fast_exp2(x[j] - m_safe);
-            sum += x[j];
-          }
-          uint8_t* dst = sP + (g >> 1) * (TILE_Q * 128);
+          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(fmaf(x[j], sl2, -m_safe)); sum += x[j]; }
+        } else {
 #pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
+          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(x[j] - m_safe); sum += x[j]; }
+        }
+        l_run = l_run * alpha + sum;
+        m_run = mx;
+        // P(c) -> smem buffer sb (its previous reader, PV(c-2), retired before iteration c-1 ended)
+        {
+          uint8_t* dst = sP + sb * SP2_BYTES;
+#pragma unroll
+          for (int cc = 0; cc < CH / 8; ++cc) {
             uint4 u;
             u.x = pack_h2(x[cc * 8 + 0], x[cc * 8 + 1], bf16);
             u.y = pack_h2(x[cc * 8 + 2], x[cc * 8 + 3], bf16);
             u.z = pack_h2(x[cc * 8 + 4], x[cc * 8 + 5], bf16);
             u.w = pack_h2(x[cc * 8 + 6], x[cc * 8 + 7], bf16);
-            *reinterpret_cast<uint4*>(dst + sw128_off(wtid, (g & 1) * 4 + cc)) = u;
+            *reinterpret_cast<uint4*>(dst + sw128_off(wtid, cc)) = u;
           }
         }
-        l_run = l_run * alpha + sum;
-        m_run = mx;
         fence_proxy_async_smem();
         tc_fence_before_sync();
         wg_barrier(wg);
-        if (wtid == 0) {
+        if (wtid == 0) issue_pv(c);
+        // ---- fold the previous chunk's O into the running output -------------------------
+        if (c > 0) {
+          const int ob = (c - 1) & 1;
+          mbar_wait(&bar_o[wg][ob], ph_o[ob]);
+          ph_o[ob] ^= 1;
           tc_fence_after_sync();
-          const uint32_t sa = smem_u32(sP);
-          const uint32_t sv = smem_u32(sV + c * SK_BYTES);
-#pragma unroll
-          for (int ks = 0; ks < CHUNK / 16; ++ks) {
-            const uint64_t da = make_smem_desc(sa + (ks >> 2) * (TILE_Q * 128) + (ks & 3) * 32, 16, 1024, LAYOUT_SW128);
-            const uint64_t db = make_smem_desc(sv + ks * 16 * 64, 512, 512, LAYOUT_SW64);
-            umma_f16(tmem_base + CHUNK, da, db, a.idesc_pv, ks ? 1u : 0u);
-          }
-          umma_commit(bo);
-        }
-        mbar_wait(bo, ph_o);
-        ph_o ^= 1;
-        tc_fence_after_sync();
-        {
           uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + CHUNK, r);
+          tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, r);
           tmem_ld_wait();
 #pragma unroll
-          for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha, __uint_as_float(r[d]));
+          for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(r[d]));
+          tc_fence_before_sync();
         }
+        alpha_prev = alpha;
+      }
+      {   // last chunk
+        const int ob = (n_ch - 1) & 1;
+        mbar_wait(&bar_o[wg][ob], ph_o[ob]);
+        ph_o[ob] ^= 1;
+        tc_fence_after_sync();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(r[d]));
         tc_fence_before_sync();
       }
       const float inv = (l_run > 0.f) ? 1.0f / (l_run * (float)a.q_passes) : 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
-      wg_barrier(wg);   // sQ / sP are free again (all MMAs that read them have retired)
+      wg_barrier(wg);   // sQ / sP / TMEM buffers are free again (every MMA that read them has retired)
     }
 
     if (row_ok) {
@@ -637,14 +666,16 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.idesc_pv = make_idesc_f16(128, DH, bf, false, true);
   const int64_t items = (int64_t)p->B * a.n_win * p->heads * a.q_tiles;
   if (items <= 0 || items > 0x7fffffff) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bad grid");
-  if (a.n_chunks <= KV_CAP_CHUNKS) {
-    const int smem = V2_FIXED_SMEM + a.n_chunks * (2 * SK_BYTES + CHUNK * 4);
+  if (a.Lk <= KV_CAP_KEYS) {
+    const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
+    const int smem = V2_FIXED_SMEM + keys_pad * (128 + 4);
     static int attr_v2 = 0;
     if (smem > attr_v2) {
       cudaError_t e = cudaFuncSetAttribute(window_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
       attr_v2 = smem;
     }
+    a.idesc_qk = make_idesc_f16(128, CH, bf, false, false);
     const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
     window_attn_v2_kernel<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     return cobevt::check_launch("window_attn_v2_kernel");

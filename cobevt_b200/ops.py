@@ -26,6 +26,7 @@ class _Stats:
         self.launches = {"conv_gemm": 0, "window_attn": 0, "eltwise": 0}
         self.flops = {"conv_gemm": 0, "window_attn": 0, "eltwise": 0}
         self.events = []
+        self.detail = []
 
     def total_launches(self):
         return sum(self.launches.values())
@@ -41,8 +42,8 @@ STATS = _Stats()
 
 
 class _timed:
-    def __init__(self, fam, flops=0):
-        self.fam, self.flops = fam, flops
+    def __init__(self, fam, flops=0, label=""):
+        self.fam, self.flops, self.label = fam, flops, label
 
     def __enter__(self):
         STATS.launches[self.fam] += 1
@@ -56,6 +57,7 @@ class _timed:
         if STATS.profile:
             self.b.record()
             STATS.events.append((self.fam, self.a, self.b))
+            STATS.detail.append((self.fam, self.label, self.flops, self.a, self.b))
         return False
 
 
@@ -156,7 +158,8 @@ def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=
     p.ln_gamma, p.ln_beta = _ptr(ln_gamma), _ptr(ln_beta)
     p.in_upsample = 1 if in_upsample else 0
     p.act, p.dtype, p.block_n, p.ln_eps = act, dtype_code(x.dtype), pc.block_n, ln_eps
-    with _timed("conv_gemm", 2 * M * pc.k_alg * pc.cout):
+    with _timed("conv_gemm", 2 * M * pc.k_alg * pc.cout,
+                f"M={M} K={pc.K} N={pc.cout} k{pc.kh}x{pc.kw} s{sh} bn{pc.block_n} in{H}x{W}x{Cin}"):
         _lib.check(_lib.lib().cobevt_conv2d_nhwc_fwd(ctypes.byref(p), _stream()), "cobevt_conv2d_nhwc_fwd")
     return y, y32, yln
 
@@ -218,7 +221,8 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p.q_stride, p.kv_stride, p.out_stride = qs, ks, C
     n_win = (qmap.H // qmap.w1) * (qmap.W // qmap.w2)
     lq, lk = qmap.views * qmap.w1 * qmap.w2, kvmap.views * kvmap.w1 * kvmap.w2
-    with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32):
+    with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32,
+                f"B={B} win={n_win} heads={heads} Lq={lq} Lk={lk} mean={int(bool(q_mean))} bias={bias is not None}"):
         _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
     return out
 
