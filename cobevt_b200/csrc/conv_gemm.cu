@@ -33,6 +33,7 @@
 #include "sm100.cuh"
 #include "common.h"
 #include <cstring>
+#include <cstdlib>
 
 using namespace sm100;
 
@@ -44,17 +45,19 @@ constexpr int A_GATHER_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
 constexpr int A_HALO_BYTES = 24 * 1024;                // 180 rows x 128 B = 23040, padded to 1 KB multiple
 constexpr int NUM_THREADS = 448;
-constexpr int LAG_GATHER = 4, LAG_HALO = 2;
+constexpr int SA_GATHER = 6, SA_HALO = 4;       // A ring depth (all stages may be in flight)
 constexpr int kMaxDynSmem = 227 * 1024 - 8192;         // static smem (barriers, bias, LN exchange) counts too
 constexpr int MAX_STAGES = 8;
 
-enum { MODE_GATHER = 0, MODE_HALO = 1 };
+enum { MODE_GATHER = 0, MODE_HALO = 1, MODE_LINEAR = 2 };
 
 struct KArgs {
   CobevtConvParams p;
   int32_t M, K, KB, n_tiles, m_tiles, total_tiles;
   int32_t mode, sa, sb, resident_b;
   int32_t tiles_y, tiles_x, nslab;      // HALO geometry
+  int32_t cin_log2, kw_magic;           // GATHER tap decode without divisions (cin_log2 < 0: generic)
+  int32_t dbg;                          // COBEVT_CONV_DEBUG bits (profiling experiments only): 1 no epilogue I/O, 2 no A loads, 4 no MMA
   uint32_t idesc;
 };
 
@@ -69,9 +72,32 @@ __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// max(x, 0) on a packed pair
+__device__ __forceinline__ uint32_t relu2(uint32_t u, int bf16) {
+  if (bf16) {
+    __nv_bfloat162 h = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&u), __float2bfloat162_rn(0.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __hmax2(*reinterpret_cast<__half2*>(&u), __float2half2_rn(0.f));
+  return *reinterpret_cast<uint32_t*>(&h);
+}
 __device__ __forceinline__ float2 unpack2(uint32_t u, int bf16) {
   if (bf16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
   return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+// tcgen05.mma with descriptors given as (lo, hi) 32-bit halves: only `lo` (start address field)
+// changes between MMAs, so the issuing thread does one integer add per operand.
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                          uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 
 // output row (TMEM lane) -> linear output pixel index, or -1
@@ -109,7 +135,8 @@ __device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&r)[U]) {
 template <int BN>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a) {
   constexpr int kBStage = BN * BLOCK_K * 2;
-  constexpr int kTmemCols = (2 * BN) < 32 ? 32 : 2 * BN;
+  constexpr int NACC = BN >= 256 ? 2 : 4;         // accumulator buffers in TMEM (power of two)
+  constexpr int kTmemCols = (NACC * BN) < 32 ? 32 : NACC * BN;
   constexpr int CW = BN >= 64 ? BN / 2 : BN;      // columns per epilogue warp
   constexpr int U = CW > 64 ? 64 : CW;            // columns per unit
   constexpr int NU = CW / U;
@@ -120,9 +147,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
   uint8_t* sA = smem;
   uint8_t* sB = smem + SA * a_stage_bytes;
   __shared__ uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES];
-  __shared__ uint64_t acc_full[2], acc_empty[2], b_res_full;
+  __shared__ uint64_t acc_full[4], acc_empty[4], b_res_full;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float sBias[512], sGamma[128], sBeta[128];
+  __shared__ __align__(16) float sBias[512], sGamma[128], sBeta[128];
   __shared__ float2 sXch[2][2][128];              // [tile parity][column half][row] = (mean, M2)
 
   const CobevtConvParams& p = a.p;
@@ -136,8 +163,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 8); mbar_init(&acc_empty[1], 8);
+    for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(&b_res_full, 1);
     mbar_fence_init();
   }
@@ -159,8 +185,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
     // ================================ A producers ========================================
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
     uint32_t it = 0;   // stage uses issued so far (across tiles)
-    if (a.mode == MODE_GATHER) {
-      constexpr int LAG = LAG_GATHER;
+    int ps = 0;        // stage of use `it`            (incremental: no runtime divisions in the loops)
+    uint32_t pph = 1;  // parity to wait for on a_empty[ps]
+    auto next_stage = [&]() { if (++ps == SA) { ps = 0; pph ^= 1u; } };
+    if (a.mode == MODE_LINEAR) {
+      // 1x1 / stride 1: A rows are contiguous token rows, no coordinate arithmetic at all
+      const int c8 = tid & 7, r0 = tid >> 3;
+      const int64_t row_bytes = (int64_t)p.Cin * 2;
+      for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / a.n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const uint8_t* base = xbytes + (int64_t)m0 * row_bytes + c8 * 16;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = ps;
+          mbar_wait(&a_empty[s], pph);
+          next_stage();
+          const bool kvalid = kb * BLOCK_K + c8 * 8 < a.K;
+          uint8_t* dst = sA + s * A_GATHER_BYTES;
+          const uint8_t* src = base + kb * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 16 * i;
+            const bool ok = kvalid && (m0 + r) < a.M;
+            if (!(a.dbg & 2)) cp_async16(dst + sw128_off(r, c8), ok ? src + r * row_bytes : xbytes, ok ? 16u : 0u);
+          }
+          cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
+        }
+      }
+    } else if (a.mode == MODE_GATHER) {
       const int Hlog = p.in_upsample ? p.Hin * 2 : p.Hin;
       const int Wlog = p.in_upsample ? p.Win * 2 : p.Win;
       const int c8 = tid & 7, r0 = tid >> 3;
@@ -181,15 +233,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
           ix0[i] = ox * p.stride_w - p.pad_w;
         }
         for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % SA;
-          mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1u);
+          const int s = ps;
+          mbar_wait(&a_empty[s], pph);
+          next_stage();
           // chunk -> (tap, channel offset)
           const int k = kb * BLOCK_K + c8 * 8;
           const bool kvalid = k < a.K;
           const int kk = kvalid ? k : 0;
-          const int tap = kk / p.Cin;
-          const int coff = kk - tap * p.Cin;
-          const int ky = tap / p.KW, kx = tap - ky * p.KW;
+          int tap, coff, ky;
+          if (a.cin_log2 >= 0) {      // power-of-two Cin, small KW: shifts + multiply-high
+            tap = kk >> a.cin_log2;
+            coff = kk & (p.Cin - 1);
+            ky = (tap * a.kw_magic) >> 16;
+          } else {
+            tap = kk / p.Cin;
+            coff = kk - tap * p.Cin;
+            ky = tap / p.KW;
+          }
+          const int kx = tap - ky * p.KW;
           uint8_t* dst = sA + s * A_GATHER_BYTES;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -198,24 +259,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             const bool ok = kvalid && iy >= 0 && iy < Hlog && ix >= 0 && ix < Wlog;
             if (p.in_upsample) { iy >>= 1; ix >>= 1; }
             const int64_t off = ((int64_t)(pixbase[i] + iy * p.Win + ix) * p.Cin + coff) * 2;
-            cp_async16(dst + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
+            if (!(a.dbg & 2)) cp_async16(dst + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
           }
-          cp_async_commit();
-          if (it >= LAG) {
-            cp_async_wait<LAG>();
-            fence_proxy_async_smem();
-            mbar_arrive(&a_full[(it - LAG) % SA]);
-          }
+          cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
         }
       }
-      // drain the last (up to LAG) groups
-      if (it >= 4) { cp_async_wait<3>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 4) % SA]); }
-      if (it >= 3) { cp_async_wait<2>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 3) % SA]); }
-      if (it >= 2) { cp_async_wait<1>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 2) % SA]); }
-      if (it >= 1) { cp_async_wait<0>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 1) % SA]); }
     } else {
       // HALO: 180 halo pixels x 8 chunks = 1440 pieces per 64-channel slab, 12 per thread
-      constexpr int LAG = LAG_HALO;
       const int per_img = a.tiles_y * a.tiles_x;
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
         const int m_tile = tile / a.n_tiles;
@@ -233,8 +283,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
           poff[i] = ok ? ((n * p.Hin + iy) * p.Win + ix) * p.Cin : -1;
         }
         for (int slab = 0; slab < a.nslab; ++slab, ++it) {
-          const int s = it % SA;
-          mbar_wait(&a_empty[s], ((it / SA) & 1) ^ 1u);
+          const int s = ps;
+          mbar_wait(&a_empty[s], pph);
+          next_stage();
           uint8_t* dst = sA + s * A_HALO_BYTES;
 #pragma unroll
           for (int i = 0; i < 12; ++i) {
@@ -243,19 +294,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             if (pix < HALO_H * HALO_W) {
               const bool ok = poff[i] >= 0;
               const int64_t off = ((int64_t)(ok ? poff[i] : 0) + slab * 64 + chunk * 8) * 2;
-              cp_async16(dst + pix * 128 + ((chunk ^ (pix & 7)) << 4), xbytes + (ok ? off : 0), ok ? 16u : 0u);
+              if (!(a.dbg & 2)) cp_async16(dst + pix * 128 + ((chunk ^ (pix & 7)) << 4), xbytes + (ok ? off : 0), ok ? 16u : 0u);
             }
           }
-          cp_async_commit();
-          if (it >= LAG) {
-            cp_async_wait<LAG>();
-            fence_proxy_async_smem();
-            mbar_arrive(&a_full[(it - LAG) % SA]);
-          }
+          cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
         }
       }
-      if (it >= 2) { cp_async_wait<1>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 2) % SA]); }
-      if (it >= 1) { cp_async_wait<0>(); fence_proxy_async_smem(); mbar_arrive(&a_full[(it - 1) % SA]); }
     }
   } else if (warp < 12) {
     // ================================ epilogue (8 warps) =================================
@@ -270,10 +314,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
       const int m_tile = tile / a.n_tiles;
       const int n_tile = tile - m_tile * a.n_tiles;
-      const int buf = acc_it & 1;
-      mbar_wait(&acc_full[buf], (acc_it >> 1) & 1);
+      const int buf = acc_it & (NACC - 1);
+      mbar_wait(&acc_full[buf], (acc_it / NACC) & 1);
       tc_fence_after_sync();
       if (!active) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+        continue;
+      }
+      if (a.dbg & 8) {   // profiling experiment: no TMEM read / math at all
+        tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
@@ -294,10 +344,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        const bool live = row_ok && n0 < p.Cout;
+        const bool live = row_ok && n0 < p.Cout && !(a.dbg & 1);
         float v[U];
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(sBias + (n0 & 511));   // broadcast LDS.128
 #pragma unroll
-        for (int j = 0; j < U; ++j) v[j] = __uint_as_float(r[j]) + sBias[(n0 + j) & 511];
+          for (int j = 0; j < U; j += 4) {
+            const float4 bb = b4[j >> 2];
+            v[j] = __uint_as_float(r[j]) + bb.x;
+            v[j + 1] = __uint_as_float(r[j + 1]) + bb.y;
+            v[j + 2] = __uint_as_float(r[j + 2]) + bb.z;
+            v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
+          }
+        }
         if (live && p.res) {
           const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
 #pragma unroll
@@ -331,7 +390,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             }
           }
         }
-        if (p.act == COBEVT_ACT_RELU) {
+        const bool relu_packed = p.act == COBEVT_ACT_RELU && !p.y32 && !do_ln;   // max(.,0) on packed pairs
+        if (p.act == COBEVT_ACT_RELU && !relu_packed) {
 #pragma unroll
           for (int j = 0; j < U; ++j) v[j] = fmaxf(v[j], 0.f);
         } else if (p.act == COBEVT_ACT_GELU) {
@@ -348,11 +408,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
               w.y = pack2(v[j + 2], v[j + 3], bf16);
               w.z = pack2(v[j + 4], v[j + 5], bf16);
               w.w = pack2(v[j + 6], v[j + 7], bf16);
+              if (relu_packed) { w.x = relu2(w.x, bf16); w.y = relu2(w.y, bf16); w.z = relu2(w.z, bf16); w.w = relu2(w.w, bf16); }
               *reinterpret_cast<uint4*>(yp + j * 2) = w;
             } else {
               for (int t = 0; t < 8; ++t)
                 if (n0 + j + t < p.Cout) {
-                  const uint32_t w = pack2(v[j + t], 0.f, bf16);
+                  const uint32_t w = pack2(relu_packed ? fmaxf(v[j + t], 0.f) : v[j + t], 0.f, bf16);
                   *reinterpret_cast<uint16_t*>(yp + (j + t) * 2) = (uint16_t)(w & 0xFFFFu);
                 }
             }
@@ -379,7 +440,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             float m2 = 0.f;
 #pragma unroll
             for (int j = 0; j < U; ++j) { const float d = v[j] - mh; m2 += d * d; }
-            const int par = acc_it & 1;
+            const int par = acc_it & 1;   // exchange slots are double-buffered independently of NACC
             sXch[par][hf][row] = make_float2(mh, m2);
             asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory");
             const float2 o = sXch[par][hf ^ 1][row];
@@ -413,16 +474,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
         mbar_arrive_expect_tx(&b_res_full, (uint32_t)(KB * kBStage));
         for (int kb = 0; kb < KB; ++kb) bulk_g2s(sB + kb * kBStage, wbase + (int64_t)kb * kBStage, kBStage, &b_res_full);
       } else {
-        uint32_t it = 0;
+        int bs = 0;
+        uint32_t bph = 1;
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
           const int n_tile = tile % a.n_tiles;
           const uint8_t* wb = wbase + (int64_t)n_tile * KB * kBStage;
-          for (int j = 0; j < KB; ++j, ++it) {
+          int slab = 0, tap = 0;
+          for (int j = 0; j < KB; ++j) {
             // consumption order: GATHER kb = j; HALO (slab-major, taps inner) kb = tap*nslab + slab
             int kb = j;
-            if (a.mode == MODE_HALO) { const int slab = j / 9, tap = j - slab * 9; kb = tap * a.nslab + slab; }
-            const int s = it % SB;
-            mbar_wait(&b_empty[s], ((it / SB) & 1) ^ 1u);
+            if (a.mode == MODE_HALO) { kb = tap * a.nslab + slab; if (++tap == 9) { tap = 0; ++slab; } }
+            const int s = bs;
+            mbar_wait(&b_empty[s], bph);
+            if (++bs == SB) { bs = 0; bph ^= 1u; }
             mbar_arrive_expect_tx(&b_full[s], kBStage);
             bulk_g2s(sB + s * kBStage, wb + (int64_t)kb * kBStage, kBStage, &b_full[s]);
           }
@@ -432,69 +496,73 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
   } else if (warp == 13) {
     // ================================ MMA issuer ==========================================
     if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
-      // descriptor templates: only the 14-bit start-address field changes per MMA
-      const uint64_t dA_gather = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
-      const uint64_t dA_halo = make_smem_desc(0, 16, HALO_W * 128, LAYOUT_SW128);
-      const uint64_t dB = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      uint32_t acc_it = 0;
+      int sa_ = 0, sb_ = 0;            // current A / B stage and the parity to wait for
+      uint32_t aph = 0, bph = 0;
+      // descriptor halves: `hi` is constant, `lo` = start address >> 4 | LBO field
+      const uint64_t tA_g = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const uint64_t tA_h = make_smem_desc(0, 16, HALO_W * 128, LAYOUT_SW128);
+      const uint32_t lo0 = (uint32_t)tA_g;                 // LBO bits only (same for all three)
+      const uint32_t hiA_g = (uint32_t)(tA_g >> 32), hiA_h = (uint32_t)(tA_h >> 32), hiB = hiA_g;
+      const uint32_t idesc = a.idesc;
       if (a.resident_b) mbar_wait(&b_res_full, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
-        const int buf = acc_it & 1;
-        mbar_wait(&acc_empty[buf], ((acc_it >> 1) & 1) ^ 1u);
+        const int buf = acc_it & (NACC - 1);
+        mbar_wait(&acc_empty[buf], ((acc_it / NACC) & 1) ^ 1u);
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * BN;
-        uint32_t first = 1;
-        if (a.mode == MODE_GATHER) {
-          for (int kb = 0; kb < KB; ++kb, ++a_it) {
-            const int sa_ = a_it % SA;
-            mbar_wait(&a_full[sa_], (a_it / SA) & 1);
+        uint32_t accum = 0;
+        if (a.mode != MODE_HALO) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait(&a_full[sa_], aph);
+            fence_proxy_async_smem();     // cp.async (generic proxy) bytes -> visible to the UMMA (async proxy)
             uint32_t sb_addr;
-            int sb_ = 0;
             if (a.resident_b) {
               sb_addr = smem_u32(sB + kb * kBStage);
             } else {
-              sb_ = b_it % SB;
-              mbar_wait(&b_full[sb_], (b_it / SB) & 1);
+              mbar_wait(&b_full[sb_], bph);
               sb_addr = smem_u32(sB + sb_ * kBStage);
             }
             tc_fence_after_sync();
-            const uint32_t sa_addr = smem_u32(sA + sa_ * A_GATHER_BYTES);
+            const uint32_t a_lo = lo0 | (smem_u32(sA + sa_ * A_GATHER_BYTES) >> 4);
+            const uint32_t b_lo = lo0 | (sb_addr >> 4);
 #pragma unroll
             for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-              umma_f16(d_tmem, dA_gather | (uint64_t)(((sa_addr + ks * 32) >> 4) & 0x3FFF),
-                       dB | (uint64_t)(((sb_addr + ks * 32) >> 4) & 0x3FFF), a.idesc, first ? 0u : 1u);
-              first = 0;
+              if (!(a.dbg & 4)) umma_lohi(d_tmem, a_lo + ks * 2, hiA_g, b_lo + ks * 2, hiB, idesc, accum);
+              accum = 1;
             }
             umma_commit(&a_empty[sa_]);
-            if (!a.resident_b) { umma_commit(&b_empty[sb_]); ++b_it; }
+            if (++sa_ == SA) { sa_ = 0; aph ^= 1u; }
+            if (!a.resident_b) { umma_commit(&b_empty[sb_]); if (++sb_ == SB) { sb_ = 0; bph ^= 1u; } }
           }
         } else {
-          for (int slab = 0; slab < a.nslab; ++slab, ++a_it) {
-            const int sa_ = a_it % SA;
-            mbar_wait(&a_full[sa_], (a_it / SA) & 1);
-            const uint32_t sa_addr = smem_u32(sA + sa_ * A_HALO_BYTES);
+          const uint32_t tap_stride = (uint32_t)(a.nslab * kBStage) >> 4;     // resident B: next tap, same slab
+          for (int slab = 0; slab < a.nslab; ++slab) {
+            mbar_wait(&a_full[sa_], aph);
+            fence_proxy_async_smem();
+            tc_fence_after_sync();
+            const uint32_t a_lo = lo0 | (smem_u32(sA + sa_ * A_HALO_BYTES) >> 4);
+            uint32_t b_res_lo = lo0 | (smem_u32(sB + slab * kBStage) >> 4);
+#pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
-              uint32_t sb_addr;
-              int sb_ = 0;
-              if (a.resident_b) {
-                sb_addr = smem_u32(sB + (tap * a.nslab + slab) * kBStage);
-              } else {
-                sb_ = b_it % SB;
-                mbar_wait(&b_full[sb_], (b_it / SB) & 1);
-                sb_addr = smem_u32(sB + sb_ * kBStage);
+              uint32_t b_lo = b_res_lo;
+              const int sb_cur = sb_;
+              if (!a.resident_b) {
+                mbar_wait(&b_full[sb_], bph);
+                tc_fence_after_sync();
+                b_lo = lo0 | (smem_u32(sB + sb_ * kBStage) >> 4);
               }
-              tc_fence_after_sync();
-              const int ky = tap / 3, kx = tap - ky * 3;
-              const uint32_t a_tap = sa_addr + (ky * HALO_W + kx) * 128;
+              constexpr int kTapRows[9] = {0, 1, 2, HALO_W, HALO_W + 1, HALO_W + 2, 2 * HALO_W, 2 * HALO_W + 1, 2 * HALO_W + 2};
 #pragma unroll
               for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-                umma_f16(d_tmem, dA_halo | (uint64_t)(((a_tap + ks * 32) >> 4) & 0x3FFF),
-                         dB | (uint64_t)(((sb_addr + ks * 32) >> 4) & 0x3FFF), a.idesc, first ? 0u : 1u);
-                first = 0;
+                if (!(a.dbg & 4)) umma_lohi(d_tmem, a_lo + kTapRows[tap] * 8 + ks * 2, hiA_h, b_lo + ks * 2, hiB, idesc, accum);
+                accum = 1;
               }
-              if (!a.resident_b) { umma_commit(&b_empty[sb_]); ++b_it; }
+              if (!a.resident_b) { umma_commit(&b_empty[sb_cur]); if (++sb_ == SB) { sb_ = 0; bph ^= 1u; } }
+              b_res_lo += tap_stride;
             }
             umma_commit(&a_empty[sa_]);
+            if (++sa_ == SA) { sa_ = 0; aph ^= 1u; }
           }
         }
         umma_commit(&acc_full[buf]);
@@ -514,7 +582,7 @@ int launch(KArgs& a, cudaStream_t st) {
   constexpr int kBStage = BN * BLOCK_K * 2;
   const int a_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
   const int budget = kMaxDynSmem - 1024;
-  a.sa = a.mode == MODE_HALO ? LAG_HALO + 2 : LAG_GATHER + 2;   // SA > LAG + 1: producers never wait on the MMA
+  a.sa = a.mode == MODE_HALO ? SA_HALO : SA_GATHER;
   const int64_t b_all = (int64_t)a.KB * kBStage;
   a.resident_b = (a.n_tiles == 1 && b_all <= budget - a.sa * a_bytes && b_all < (1 << 20)) ? 1 : 0;
   int64_t smem;
@@ -524,7 +592,7 @@ int launch(KArgs& a, cudaStream_t st) {
   } else {
     int sb = (budget - a.sa * a_bytes) / kBStage;
     if (sb > MAX_STAGES) sb = MAX_STAGES;
-    if (sb < 2) { a.sa = (a.mode == MODE_HALO ? LAG_HALO : LAG_GATHER) + 1; sb = (budget - a.sa * a_bytes) / kBStage; }
+    if (sb < 2) { a.sa = 2; sb = (budget - a.sa * a_bytes) / kBStage; }
     if (sb < 2) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: no smem for the B ring (BN=%d)", BN);
     a.sb = sb;
     smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
@@ -612,10 +680,20 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
     a.nslab = p->Cin / 64;
     a.m_tiles = p->N * a.tiles_y * a.tiles_x;
   } else {
-    a.mode = MODE_GATHER;
+    const bool linear = p->KH == 1 && p->KW == 1 && p->stride_h == 1 && p->stride_w == 1 && p->pad_h == 0 &&
+                        p->pad_w == 0 && !p->in_upsample;
+    a.mode = linear ? MODE_LINEAR : MODE_GATHER;
     a.m_tiles = cobevt::ceil_div(a.M, BLOCK_M);
+    a.cin_log2 = -1;
+    if ((p->Cin & (p->Cin - 1)) == 0 && p->KW <= 16 && p->KH * p->KW < 4096) {
+      int l = 0;
+      while ((1 << l) < p->Cin) ++l;
+      a.cin_log2 = l;
+      a.kw_magic = (65536 + p->KW - 1) / p->KW;
+    }
   }
   a.total_tiles = a.m_tiles * a.n_tiles;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->block_n) {
     case 16: return launch<16>(a, st);

@@ -185,6 +185,11 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uin
                "l"(gsrc), "r"(src_bytes)
                : "memory");
 }
+// Arrive on an mbarrier when all cp.async issued so far by this thread have landed (the arrival
+// is counted against the barrier's expected count: .noinc).  No thread waits for its own loads.
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {

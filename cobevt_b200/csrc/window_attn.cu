@@ -327,8 +327,9 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
 // =====================================================================================
 // Resident-KV kernel: one CTA per (batch row, window, head).  The window's K/V (<= 1024 keys) are
 // loaded ONCE into shared memory; two independent 128-thread warpgroups walk over the 128-row
-// query tiles / query views.  Inside a warpgroup the tensor-core work is software-pipelined over
-// 64-key chunks so no MMA latency sits on the exp critical path:
+// query tiles / query views; each warpgroup has its own MMA-issuing thread (warps 8 / 9) and talks to
+// it only through mbarriers -- the softmax threads never wait for each other.  The tensor-core work is
+// software-pipelined over 64-key chunks so no MMA latency sits on the exp critical path:
 //     iteration c:  issue S(c+1)=Q K(c+1)^T  |  softmax of S(c) (held in 64 registers)  |
 //                   issue O(c)=P(c) V(c)     |  fold the finished O(c-1) into the running output
 // S and O are double-buffered in TMEM (2x64 + 2x32 columns per warpgroup), P in shared memory.
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
 // =====================================================================================
 constexpr int CH = 64;                                 // keys per chunk
 constexpr int KV_CAP_KEYS = 1024;
-constexpr int V2_THREADS = 256;
+constexpr int V2_THREADS = 320;   // 2 softmax warpgroups + 2 MMA-issuer warps
 constexpr int SP2_BYTES = TILE_Q * CH * 2;             // 16 KB per P buffer
 constexpr int V2_FIXED_SMEM = 1024 + 2 * SQ_BYTES + 2 * 2 * SP2_BYTES;   // + keys * (128 B K/V + 4 B mask)
 
@@ -345,6 +346,7 @@ __device__ __forceinline__ void wg_barrier(int wg) {
 }
 
 __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AArgs a) {
+  // roles: warps 0-3 = softmax group 0, warps 4-7 = softmax group 1, warp 8 / 9 lane 0 = their MMA issuers
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_ch = (a.Lk + CH - 1) / CH;
@@ -354,12 +356,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   uint8_t* sK = sP_all + 4 * SP2_BYTES;
   uint8_t* sV = sK + keys_pad * 64;
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
-  __shared__ uint64_t bar_s[2][2], bar_o[2][2];
+  __shared__ uint64_t bar_s[2][2], bar_o[2][2], bar_p[2][2], bar_q[2];
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = warp >> 2, wtid = tid & 127;
+  const bool is_mma = warp >= 8;
+  const int wg = is_mma ? warp - 8 : warp >> 2, wtid = tid & 127;
   int item = blockIdx.x;
   const int head = item % p.heads; item /= p.heads;
   const int win = item % a.n_win;
@@ -370,7 +373,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); }
+      for (int j = 0; j < 2; ++j) { mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); mbar_init(&bar_p[i][j], 128); }
+    mbar_init(&bar_q[0], 128); mbar_init(&bar_q[1], 128);
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -417,35 +421,70 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s + wg * 256;   // S0 [0,64) S1 [64,128) O0 [128,160) O1 [160,192)
-  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint8_t* sQ = sQ_all + wg * SQ_BYTES;
   uint8_t* sP = sP_all + wg * 2 * SP2_BYTES;
+  const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
+
+  if (is_mma) {
+    // =============================== MMA issuer of warpgroup `wg` ===========================
+    if ((tid & 31) == 0) {
+      const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
+      const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+      const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);
+      const uint32_t qk_lo = (uint32_t)dQK, qk_hi = (uint32_t)(dQK >> 32);
+      const uint32_t p_lo = (uint32_t)dP, p_hi = (uint32_t)(dP >> 32);
+      const uint32_t v_lo = (uint32_t)dV, v_hi = (uint32_t)(dV >> 32);
+      const uint32_t q_addr = smem_u32(sQ) >> 4, k_addr = smem_u32(sK) >> 4, v_addr = smem_u32(sV) >> 4;
+      const uint32_t p_addr = smem_u32(sP) >> 4;
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
+      };
+      auto issue_qk = [&](int c) {       // S(c) = Q K(c)^T  -> S buffer c&1
+        const uint32_t kb = k_addr + c * (CH * 64 / 16);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma(tmem_base + (c & 1) * CH, qk_lo | (q_addr + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
+        umma_commit(&bar_s[wg][c & 1]);
+      };
+      auto issue_pv = [&](int c) {       // O(c) = P(c) V(c)  -> O buffer c&1
+        const uint32_t pa = p_addr + (c & 1) * (SP2_BYTES / 16), va = v_addr + c * (CH * 64 / 16);
+#pragma unroll
+        for (int ks = 0; ks < CH / 16; ++ks)
+          mma(tmem_base + 2 * CH + (c & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
+        umma_commit(&bar_o[wg][c & 1]);
+      };
+      uint32_t ph_q = 0, ph_p[2] = {0, 0};
+      for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
+        for (int pass = 0; pass < a.q_passes; ++pass) {
+          mbar_wait(&bar_q[wg], ph_q);
+          ph_q ^= 1;
+          tc_fence_after_sync();
+          issue_qk(0);
+          if (n_ch > 1) issue_qk(1);
+          for (int c = 0; c < n_ch; ++c) {
+            mbar_wait(&bar_p[wg][c & 1], ph_p[c & 1]);     // P(c) written, S(c) consumed, O(c-2) folded
+            ph_p[c & 1] ^= 1;
+            tc_fence_after_sync();
+            issue_pv(c);
+            if (c + 2 < n_ch) issue_qk(c + 2);
+          }
+        }
+      }
+    }
+  } else {
+  // =============================== softmax warpgroup `wg` ==================================
+  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   uint32_t ph_s[2] = {0, 0}, ph_o[2] = {0, 0};
   const float sl2 = p.scale * 1.4426950408889634f;
-  const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
   const bool any_mask = p.key_mask != nullptr;
   const bool bias_vec = (a.Lk & 3) == 0;
-  const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
-  const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
-  const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);
-  auto desc_at = [](uint64_t d, uint32_t addr) { return d | (uint64_t)((addr >> 4) & 0x3FFF); };
-
-  auto issue_qk = [&](int c) {       // S(c) = Q K(c)^T  -> S buffer c&1
-    tc_fence_after_sync();
-    const uint32_t sa = smem_u32(sQ), sb = smem_u32(sK + c * CH * 64);
-#pragma unroll
-    for (int ks = 0; ks < DH / 16; ++ks)
-      umma_f16(tmem_base + (c & 1) * CH, desc_at(dQK, sa + ks * 32), desc_at(dQK, sb + ks * 32), a.idesc_qk, ks ? 1u : 0u);
-    umma_commit(&bar_s[wg][c & 1]);
-  };
-  auto issue_pv = [&](int c) {       // O(c) = P(c) V(c)  -> O buffer c&1
-    tc_fence_after_sync();
-    const uint32_t sa = smem_u32(sP + (c & 1) * SP2_BYTES), sv = smem_u32(sV + c * CH * 64);
-#pragma unroll
-    for (int ks = 0; ks < CH / 16; ++ks)
-      umma_f16(tmem_base + 2 * CH + (c & 1) * DH, desc_at(dP, sa + ks * 32), desc_at(dV, sv + ks * 16 * 64), a.idesc_pv, ks ? 1u : 0u);
-    umma_commit(&bar_o[wg][c & 1]);
-  };
+  bool first_q = true;
 
   for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
     const int qrow = q_tile * TILE_Q + wtid;
@@ -455,7 +494,9 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     for (int d = 0; d < DH; ++d) acc[d] = 0.f;
 
     for (int pass = 0; pass < a.q_passes; ++pass) {
-      // ---- Q tile: 4 lanes per row ----------------------------------------------------
+      // ---- Q tile: 4 lanes per row.  Every MMA that read the previous Q / P / S / O has retired:
+      //      this thread waited on the last s_ready and o_ready of the previous pass. -------------
+      (void)first_q;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = wtid + 128 * i;
@@ -476,8 +517,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       cp_async_wait<0>();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      wg_barrier(wg);
-      if (wtid == 0) issue_qk(0);
+      mbar_arrive(&bar_q[wg]);
 
       float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
       float o[DH];
@@ -486,7 +526,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
 
       for (int c = 0; c < n_ch; ++c) {
         const int sb = c & 1;
-        if (wtid == 0 && c + 1 < n_ch) issue_qk(c + 1);
         const int key0 = c * CH;
         const bool use_km = any_mask || (key0 + CH > a.Lk);
         mbar_wait(&bar_s[wg][sb], ph_s[sb]);
@@ -505,10 +544,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         float mx;
         const bool plain = !use_km && !(p.bias != nullptr);
         if (plain) {
-          float mr = x[0];
+          float mr[4] = {x[0], x[1], x[2], x[3]};          // 4 independent chains (ILP)
 #pragma unroll
-          for (int j = 1; j < CH; ++j) mr = fmaxf(mr, x[j]);
-          mx = fmaxf(m_run, mr * sl2);
+          for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+          mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2);
         } else {
           if (use_km) {
             const float4* km4 = reinterpret_cast<const float4*>(kmask + key0);
@@ -541,23 +580,25 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
                 if (key0 + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
             }
           }
-          mx = m_run;
+          float mr[4] = {x[0], x[1], x[2], x[3]};
 #pragma unroll
-          for (int j = 0; j < CH; ++j) mx = fmaxf(mx, x[j]);
+          for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+          mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
         }
         const float m_safe = (mx == -INFINITY) ? 0.f : mx;
         const float alpha = fast_exp2(m_run - m_safe);
-        float sum = 0.f;
+        float sm[4] = {0.f, 0.f, 0.f, 0.f};
         if (plain) {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(fmaf(x[j], sl2, -m_safe)); sum += x[j]; }
+          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(fmaf(x[j], sl2, -m_safe)); sm[j & 3] += x[j]; }
         } else {
 #pragma unroll
-          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(x[j] - m_safe); sum += x[j]; }
+          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(x[j] - m_safe); sm[j & 3] += x[j]; }
         }
+        const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
         l_run = l_run * alpha + sum;
         m_run = mx;
-        // P(c) -> smem buffer sb (its previous reader, PV(c-2), retired before iteration c-1 ended)
+        // P(c) -> smem buffer sb (its previous reader, PV(c-2), retired: this thread folded O(c-2))
         {
           uint8_t* dst = sP + sb * SP2_BYTES;
 #pragma unroll
@@ -572,8 +613,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
-        wg_barrier(wg);
-        if (wtid == 0) issue_pv(c);
+        mbar_arrive(&bar_p[wg][sb]);
         // ---- fold the previous chunk's O into the running output -------------------------
         if (c > 0) {
           const int ob = (c - 1) & 1;
@@ -604,7 +644,6 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       const float inv = (l_run > 0.f) ? 1.0f / (l_run * (float)a.q_passes) : 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
-      wg_barrier(wg);   // sQ / sP / TMEM buffers are free again (every MMA that read them has retired)
     }
 
     if (row_ok) {
@@ -623,6 +662,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         *reinterpret_cast<uint4*>(op + ch * 16) = u;
       }
     }
+  }
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -57,7 +57,9 @@ class ResNetPlan:
     def __init__(self, trunk, device, dtype, n_levels):
         self.dtype = dtype
         w, b = fold_conv_bn(trunk.conv1, trunk.bn1)
-        self.stem = PackedConv(w, b, device, dtype, cin_pad=8)
+        # 7x7 stem on the 8-channel padded image: one tap = one 16-byte pixel; the kernel row is padded
+        # to 8 taps so every 64-wide k-block is one contiguous 128-byte run of the input row
+        self.stem = PackedConv(w, b, device, dtype, cin_pad=8, kw_pad=8)
         self.levels = []
         for li in range(n_levels):
             blocks = []

@@ -97,7 +97,7 @@ class PackedConv:
     BatchNorm folding and channel permutations are done by the caller before packing.
     """
 
-    def __init__(self, weight, bias, device, dtype=torch.float16, cin_pad=None, block_n=None):
+    def __init__(self, weight, bias, device, dtype=torch.float16, cin_pad=None, block_n=None, kw_pad=None):
         w = weight.detach().float().cpu()
         if w.dim() == 2:
             w = w[:, :, None, None]
@@ -105,8 +105,12 @@ class PackedConv:
         cin_p = cin_pad if cin_pad is not None else (cin + 7) // 8 * 8
         if cin_p != cin:
             w = torch.cat([w, torch.zeros(cout, cin_p - cin, kh, kw)], dim=1)
-        self.cout, self.cin, self.kh, self.kw = cout, cin_p, kh, kw
         self.k_alg = kh * kw * cin            # un-padded reduction length (algorithmic FLOPs)
+        self.kw_logical = kw                  # output extent is computed from the true kernel width
+        if kw_pad is not None and kw_pad > kw:   # zero taps appended on the right (keeps k-blocks row-aligned)
+            w = torch.cat([w, torch.zeros(cout, w.shape[1], kh, kw_pad - kw)], dim=3)
+            kw = kw_pad
+        self.cout, self.cin, self.kh, self.kw = cout, cin_p, kh, kw
         self.K = kh * kw * cin_p
         self.block_n = block_n or pick_block_n(cout)
         self.dtype = dtype
@@ -137,7 +141,7 @@ def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=
     Hl, Wl = (2 * H, 2 * W) if in_upsample else (H, W)
     (sh, sw), (ph, pw) = _pair(stride), _pair(pad)
     OH = (Hl + 2 * ph - pc.kh) // sh + 1
-    OW = (Wl + 2 * pw - pc.kw) // sw + 1
+    OW = (Wl + 2 * pw - pc.kw_logical) // sw + 1
     M = N * OH * OW
     y = out if out is not None else (torch.empty((N, OH, OW, pc.cout), dtype=x.dtype, device=x.device) if want16 else None)
     y32 = torch.empty((N, OH, OW, pc.cout), dtype=torch.float32, device=x.device) if out32 else None
