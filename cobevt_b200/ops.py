@@ -242,7 +242,7 @@ def pack_rgb8(x, dtype):
     assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3
     y = torch.empty(*x.shape[:-1], 8, dtype=dtype, device=x.device)
     npix = x.numel() // 3
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "pack_rgb8"):
         _lib.check(_lib.lib().cobevt_pack_rgb8(_ptr(x), _ptr(y), npix, dtype_code(dtype), _stream()), "cobevt_pack_rgb8")
     return y
 
@@ -251,7 +251,7 @@ def maxpool3x3s2(x):
     N, H, W, C = x.shape
     OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(N, OH, OW, C, dtype=x.dtype, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "maxpool3x3s2_nhwc"):
         _lib.check(_lib.lib().cobevt_maxpool3x3s2_nhwc(_ptr(x), _ptr(y), N, H, W, C, dtype_code(x.dtype), _stream()),
                    "cobevt_maxpool3x3s2_nhwc")
     return y
@@ -262,7 +262,7 @@ def bn_relu2(x, sa, ba, sb=None, bb=None):
     rows = x.numel() // C
     ya = torch.empty_like(x)
     yb = torch.empty_like(x) if sb is not None else None
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "bn_relu2"):
         _lib.check(_lib.lib().cobevt_bn_relu2(_ptr(x), _f32(sa), _f32(ba), _ptr(ya), _ptr(sb), _ptr(bb), _ptr(yb),
                                               rows, C, dtype_code(x.dtype), _stream()), "cobevt_bn_relu2")
     return ya, yb
@@ -272,7 +272,7 @@ def ray_embed(I_inv, E_inv, w_img, w_cam, h, w, image_h, image_w, C, dtype, inve
     """I_inv: (NV,3,3) inverse intrinsics, or the intrinsics themselves with invert_intrinsic=True."""
     NV = I_inv.shape[0]
     out = torch.empty(NV, h, w, C, dtype=dtype, device=I_inv.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "ray_embed"):
         _lib.check(_lib.lib().cobevt_ray_embed(_f32(I_inv), _f32(E_inv), _f32(w_img), _f32(w_cam), _ptr(out), NV, h, w,
                                                float(image_h), float(image_w), C, 1 if invert_intrinsic else 0,
                                                dtype_code(dtype), _stream()),
@@ -285,7 +285,7 @@ def bev_query(x, world, w_bev, b_bev, w_cam, E_inv, BL, n, P, eps=1e-5):
     C = x.shape[-1]
     x_rows = x.numel() // C
     out = torch.empty(BL, n, P, C, dtype=x.dtype, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "bev_query"):
         _lib.check(_lib.lib().cobevt_bev_query(_ptr(x), x_rows, _f32(world), _f32(w_bev), _f32(b_bev), _f32(w_cam),
                                                _f32(E_inv), _ptr(out), BL, n, P, C, eps, dtype_code(x.dtype), _stream()),
                    "cobevt_bev_query")
@@ -296,7 +296,7 @@ def layernorm_rows(x, gamma=None, beta=None, eps=1e-5):
     C = x.shape[-1]
     assert x.is_contiguous()
     y = torch.empty_like(x)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "layernorm_rows"):
         _lib.check(_lib.lib().cobevt_layernorm_rows(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), x.numel() // C, C, eps,
                                                     dtype_code(x.dtype), _stream()), "cobevt_layernorm_rows")
     return y
@@ -306,7 +306,7 @@ def mean_views_ln(x, eps=1e-5):
     """x (B, L, P, C) -> (B, P, C)."""
     B, L, P, C = x.shape
     y = torch.empty(B, P, C, dtype=x.dtype, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "mean_views_ln"):
         _lib.check(_lib.lib().cobevt_mean_views_ln(_ptr(x), _ptr(y), B, L, P, C, eps, dtype_code(x.dtype), _stream()),
                    "cobevt_mean_views_ln")
     return y
@@ -318,7 +318,7 @@ def sttf_regroup(x, tm, record_len, B, L, discrete_ratio, downsample_rate, use_r
     assert tm.dtype == torch.float32 and tm.is_contiguous() and record_len.dtype == torch.int64
     out = torch.empty(B, L, H, W, C, dtype=x.dtype, device=x.device)
     mask = torch.empty(B, H, W, L, dtype=torch.uint8, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "sttf_regroup"):
         _lib.check(_lib.lib().cobevt_sttf_regroup(_ptr(x), _ptr(tm), _ptr(record_len), _ptr(out), _ptr(mask), B, L, H, W, C,
                                                   float(discrete_ratio), float(downsample_rate), 1 if use_roi_mask else 0,
                                                   dtype_code(x.dtype), _stream()), "cobevt_sttf_regroup")
@@ -335,7 +335,7 @@ def nchw_to_nhwc(x, dtype, cpad=None):
     N, C, H, W = x.shape
     cp = cpad or C
     y = torch.empty(N, H, W, cp, dtype=dtype, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "permute"):
         _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 1, _any_code(x.dtype), _any_code(dtype), _stream()),
                    "cobevt_permute")
     return y
@@ -347,7 +347,7 @@ def nhwc_to_nchw(x, dtype, c=None):
     N, H, W, cp = x.shape
     C = c or cp
     y = torch.empty(N, C, H, W, dtype=dtype, device=x.device)
-    with _timed("eltwise"):
+    with _timed("eltwise", 0, "permute"):
         _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 0, _any_code(x.dtype), _any_code(dtype), _stream()),
                    "cobevt_permute")
     return y

@@ -20,6 +20,6 @@ with torch.no_grad():
 tot = 0
 for fam, label, fl, a, b in ops.STATS.detail:
     ms = a.elapsed_time(b); tot += ms
-    if fam != "eltwise":
+    if True:
         print(f"{ms*1e3:9.1f} us {fl/1e9:8.2f} GF {fl/ms/1e9 if ms>0 else 0:8.1f} TF/s  {fam:12s} {label}")
 print("total ms", tot)
