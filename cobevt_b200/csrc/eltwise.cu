@@ -29,6 +29,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float2 warp_sum2(float a, float b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  return make_float2(a, b);
+}
+
 constexpr int MAXC_PER_LANE = 8;  // rows up to 256 channels per warp
 
 // load C/32 consecutive channels of a 16-bit row for this lane (C % 64 == 0 -> pairs)
@@ -86,6 +95,26 @@ __global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restri
   uint4 u;
   u.x = pk2(r, g, bf16); u.y = pk2(b, 0.f, bf16); u.z = 0; u.w = 0;
   *reinterpret_cast<uint4*>(y + i * 8) = u;
+}
+
+// ------------------------------------------------------------------ pack_rgb4_padded
+// (N,H,W,3) fp32 -> (N, H+pt+pb, Wp, 4) 16-bit with a zero border (pt rows on top, pl columns on the
+// left): the 7x7/s2 stem then needs no bounds checks and its taps start on 16-byte boundaries.
+__global__ void pack_rgb4_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
+                                     int Hp, int Wp, int pt, int pl, int bf16) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * Hp * Wp) return;
+  const int xp = (int)(i % Wp);
+  const int yp = (int)((i / Wp) % Hp);
+  const int n = (int)(i / ((int64_t)Wp * Hp));
+  const int ys = yp - pt, xs = xp - pl;
+  uint2 u = make_uint2(0u, 0u);
+  if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
+    const float* s = x + (((int64_t)n * H + ys) * W + xs) * 3;
+    u.x = pk2(s[0], s[1], bf16);
+    u.y = pk2(s[2], 0.f, bf16);
+  }
+  *reinterpret_cast<uint2*>(y + i * 4) = u;
 }
 
 // ------------------------------------------------------------------ maxpool 3x3 s2 p1
@@ -155,6 +184,7 @@ __global__ void bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __r
 // out = normalize(W_img d - W_cam c)   (fax_modules.py:346-358).  blockIdx.y = view; every lane
 // keeps the embedding weights of its C/32 channels in registers and the warp walks over cells.
 constexpr int CELLS_PER_BLOCK = 256;
+template <int PER>
 __global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict__ I_inv, const float* __restrict__ E_inv,
                                  const float* __restrict__ w_img, const float* __restrict__ w_cam,
                                  uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
@@ -175,11 +205,11 @@ __global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict_
   float Ei[16];
 #pragma unroll
   for (int r = 0; r < 16; ++r) Ei[r] = E_inv[v * 16 + r];
-  const int per = C / 32;
-  float wi[MAXC_PER_LANE][4], ce[MAXC_PER_LANE];
+  constexpr int per = PER;
+  float wi[PER][4], ce[PER];
 #pragma unroll
-  for (int i = 0; i < MAXC_PER_LANE; ++i) {
-    if (i < per) {
+  for (int i = 0; i < PER; ++i) {
+    {
       const int ch = lane * per + i;
       float cacc = 0.f;
 #pragma unroll
@@ -189,32 +219,42 @@ __global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict_
   }
   const int ncell = h * w;
   const int base = blockIdx.x * CELLS_PER_BLOCK;
-  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 8) {
-    const int cell = base + cc;
-    if (cell >= ncell) break;
-    const int ix = cell % w, iy = cell / w;
-    const float px = (w > 1 ? (float)ix / (float)(w - 1) : 0.f) * image_w;
-    const float py = (h > 1 ? (float)iy / (float)(h - 1) : 0.f) * image_h;
-    const float cx = Ii[0] * px + Ii[1] * py + Ii[2];
-    const float cy = Ii[3] * px + Ii[4] * py + Ii[5];
-    const float cz = Ii[6] * px + Ii[7] * py + Ii[8];
-    float d[4];
+  // two independent cells per iteration (ILP across the shuffle chains)
+  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 16) {
+    float e[2][PER];
+    float ss[2] = {0.f, 0.f};
+    int cell[2] = {base + cc, base + cc + 8};
 #pragma unroll
-    for (int r = 0; r < 4; ++r) d[r] = Ei[r * 4] * cx + Ei[r * 4 + 1] * cy + Ei[r * 4 + 2] * cz + Ei[r * 4 + 3];
-    float e[MAXC_PER_LANE];
-    float ss = 0.f;
+    for (int u = 0; u < 2; ++u) {
+      const int cl = cell[u] < ncell ? cell[u] : ncell - 1;
+      const int ix = cl % w, iy = cl / w;
+      const float px = (w > 1 ? (float)ix / (float)(w - 1) : 0.f) * image_w;
+      const float py = (h > 1 ? (float)iy / (float)(h - 1) : 0.f) * image_h;
+      const float cx = Ii[0] * px + Ii[1] * py + Ii[2];
+      const float cy = Ii[3] * px + Ii[4] * py + Ii[5];
+      const float cz = Ii[6] * px + Ii[7] * py + Ii[8];
+      float d[4];
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) {
-      if (i < per) {
-        const float a = wi[i][0] * d[0] + wi[i][1] * d[1] + wi[i][2] * d[2] + wi[i][3] * d[3] - ce[i];
-        e[i] = a;
-        ss += a * a;
+      for (int r = 0; r < 4; ++r) d[r] = Ei[r * 4] * cx + Ei[r * 4 + 1] * cy + Ei[r * 4 + 2] * cz + Ei[r * 4 + 3];
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        {
+          const float a = wi[i][0] * d[0] + wi[i][1] * d[1] + wi[i][2] * d[2] + wi[i][3] * d[3] - ce[i];
+          e[u][i] = a;
+          ss[u] += a * a;
+        }
       }
     }
-    const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
+    const float2 tot = warp_sum2(ss[0], ss[1]);
+    const float inv[2] = {__fdividef(1.0f, sqrtf(tot.x) + 1e-7f), __fdividef(1.0f, sqrtf(tot.y) + 1e-7f)};
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) e[i] *= inv;
-    store_row(out + ((int64_t)v * ncell + cell) * C, C, lane, bf16, e);
+    for (int u = 0; u < 2; ++u) {
+      if (cell[u] < ncell) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) e[u][i] *= inv[u];
+        store_row(out + ((int64_t)v * ncell + cell[u]) * C, C, lane, bf16, e[u]);
+      }
+    }
   }
 }
 
@@ -222,6 +262,7 @@ __global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict_
 // out[b, n, p, :] = LN0( x[b, p, :] + normalize(W_bev world_p + b_bev - W_cam c_{b,n}) )
 // (fax_modules.py:370-375,387-390 followed by the LayerNorm of to_q, :189,216).
 // blockIdx.y = b*n + view; lanes keep their channels' weights in registers.
+template <int PER>
 __global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restrict__ x, int64_t x_rows, const float* __restrict__ world,
                                  const float* __restrict__ w_bev, const float* __restrict__ b_bev,
                                  const float* __restrict__ w_cam, const float* __restrict__ E_inv,
@@ -231,11 +272,11 @@ __global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restri
   const int b = v / n;
   const float* Ei = E_inv + (int64_t)v * 16;
   const float c0 = Ei[3], c1 = Ei[7], c2 = Ei[11], c3 = Ei[15];
-  const int per = C / 32;
-  float wb[MAXC_PER_LANE][2], ce[MAXC_PER_LANE];
+  constexpr int per = PER;
+  float wb[PER][2], ce[PER];
 #pragma unroll
-  for (int i = 0; i < MAXC_PER_LANE; ++i) {
-    if (i < per) {
+  for (int i = 0; i < PER; ++i) {
+    {
       const int ch = lane * per + i;
       wb[i][0] = w_bev[ch * 2];
       wb[i][1] = w_bev[ch * 2 + 1];
@@ -244,34 +285,50 @@ __global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restri
   }
   const int base = blockIdx.x * CELLS_PER_BLOCK;
   const float invC = 1.0f / (float)C;
-  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 8) {
-    const int p = base + cc;
-    if (p >= P) break;
-    const float wx = world[p], wy = world[P + p];
-    float e[MAXC_PER_LANE], xv[MAXC_PER_LANE];
-    const int64_t xr = ((int64_t)b * P + p) % x_rows;
-    load_row(x + xr * C, C, lane, bf16, xv);
-    float ss = 0.f;
+  for (int cc = warp; cc < CELLS_PER_BLOCK; cc += 16) {
+    float e[2][PER];
+    float ss[2] = {0.f, 0.f};
+    int cell[2] = {base + cc, base + cc + 8};
+    float xv[2][PER];
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) {
-      if (i < per) {
-        const float a = fmaf(wb[i][0], wx, fmaf(wb[i][1], wy, ce[i]));
-        e[i] = a;
-        ss += a * a;
+    for (int u = 0; u < 2; ++u) {
+      const int pp = cell[u] < P ? cell[u] : P - 1;
+      const float wx = world[pp], wy = world[P + pp];
+      const int64_t xr = (x_rows == (int64_t)P) ? (int64_t)pp : (int64_t)b * P + pp;   // broadcast prior or per-row map
+      load_row(x + xr * C, C, lane, bf16, xv[u]);
+#pragma unroll
+      for (int i = 0; i < PER; ++i) {
+        {
+          const float a = fmaf(wb[i][0], wx, fmaf(wb[i][1], wy, ce[i]));
+          e[u][i] = a;
+          ss[u] += a * a;
+        }
       }
     }
-    const float inv = 1.0f / (sqrtf(warp_sum(ss)) + 1e-7f);
-    float s1 = 0.f;
+    const float2 nrm = warp_sum2(ss[0], ss[1]);
+    const float inv[2] = {__fdividef(1.0f, sqrtf(nrm.x) + 1e-7f), __fdividef(1.0f, sqrtf(nrm.y) + 1e-7f)};
+    float s1[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) { e[i] = fmaf(e[i], inv, xv[i]); s1 += e[i]; }
-    const float mean = warp_sum(s1) * invC;
-    float s2 = 0.f;
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) { const float dd = e[i] - mean; s2 += dd * dd; }
-    const float rstd = rsqrtf(warp_sum(s2) * invC + eps);
+      for (int i = 0; i < PER; ++i) { e[u][i] = fmaf(e[u][i], inv[u], xv[u][i]); s1[u] += e[u][i]; }
+    const float2 sm = warp_sum2(s1[0], s1[1]);
+    const float mean[2] = {sm.x * invC, sm.y * invC};
+    float s2[2] = {0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < MAXC_PER_LANE; ++i) if (i < per) e[i] = (e[i] - mean) * rstd;
-    store_row(out + ((int64_t)v * P + p) * C, C, lane, bf16, e);
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { const float dd = e[u][i] - mean[u]; s2[u] += dd * dd; }
+    const float2 vr = warp_sum2(s2[0], s2[1]);
+    const float rstd[2] = {rsqrtf(vr.x * invC + eps), rsqrtf(vr.y * invC + eps)};
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (cell[u] < P) {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) e[u][i] = (e[u][i] - mean[u]) * rstd[u];
+        store_row(out + ((int64_t)v * P + cell[u]) * C, C, lane, bf16, e[u]);
+      }
+    }
   }
 }
 
@@ -426,6 +483,14 @@ extern "C" int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t d
   return cobevt::check_launch("pack_rgb8");
 }
 
+extern "C" int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                                        int32_t pad_top, int32_t pad_left, int32_t dtype, void* stream) {
+  if (!x || !y || N <= 0 || Hp < H + pad_top || Wp < W + pad_left) return fail(COBEVT_ERR_SHAPE, "pack_rgb4_padded: bad args");
+  const int64_t total = (int64_t)N * Hp * Wp;
+  pack_rgb4_pad_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, dtype);
+  return cobevt::check_launch("pack_rgb4_padded");
+}
+
 extern "C" int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
                                          int32_t dtype, void* stream) {
   if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "maxpool: bad args");
@@ -448,8 +513,9 @@ extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const fl
                                  int32_t invert_intrinsic, int32_t dtype, void* stream) {
   if (!I_inv || !E_inv || !w_img || !w_cam || !out || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "ray_embed: bad args (C must be 64/128/256)");
   dim3 grid((h * w + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, NV);
-  ray_embed_kernel<<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w,
-                                                                     image_h, image_w, C, invert_intrinsic, dtype);
+  if (C == 128) ray_embed_kernel<4><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else if (C == 64) ray_embed_kernel<2><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else ray_embed_kernel<8><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   return cobevt::check_launch("ray_embed");
 }
 
@@ -459,8 +525,9 @@ extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* worl
   if (!x || !world || !w_bev || !b_bev || !w_cam || !E_inv || !out || !ok_c(C) || x_rows <= 0)
     return fail(COBEVT_ERR_SHAPE, "bev_query: bad args");
   dim3 grid((P + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, BL * n);
-  bev_query_kernel<<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam,
-                                                                     E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  if (C == 128) bev_query_kernel<4><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else if (C == 64) bev_query_kernel<2><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else bev_query_kernel<8><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   return cobevt::check_launch("bev_query");
 }
 

@@ -57,9 +57,16 @@ class ResNetPlan:
     def __init__(self, trunk, device, dtype, n_levels):
         self.dtype = dtype
         w, b = fold_conv_bn(trunk.conv1, trunk.bn1)
-        # 7x7 stem on the 8-channel padded image: one tap = one 16-byte pixel; the kernel row is padded
-        # to 8 taps so every 64-wide k-block is one contiguous 128-byte run of the input row
-        self.stem = PackedConv(w, b, device, dtype, cin_pad=8, kw_pad=8)
+        # 7x7/s2 stem on a zero-bordered RGBx (4-channel) image viewed as "super-pixels" of 2 pixels x 4
+        # channels = 16 bytes: (N, H+6, Wp/2, 8).  A kernel row is 4 super-taps (8 pixels, the 8th has zero
+        # weight), stride (2,1), no padding -> K = 7*4*8 = 224 (vs 392 for RGB padded to 8 channels), no
+        # bounds checks, every tap 16-byte aligned.
+        co = w.shape[0]
+        wp = torch.zeros(co, 4, 7, 8)
+        wp[:, :3, :, :7] = w                                    # (co, c, ky, kx) with c<3, kx<7
+        wp = wp.reshape(co, 4, 7, 4, 2).permute(0, 4, 1, 2, 3)   # co dx c ky kxs
+        self.stem = PackedConv(wp.reshape(co, 8, 7, 4), b, device, dtype)
+        self.stem.k_alg = 7 * 7 * 3
         self.levels = []
         for li in range(n_levels):
             blocks = []
@@ -79,8 +86,11 @@ class ResNetPlan:
 
     def run(self, images):
         """images (NI, H, W, 3) fp32 -> list of NHWC 16-bit feature maps, one per level."""
-        x = ops.pack_rgb8(images, self.dtype)
-        x, _, _ = ops.conv2d_nhwc(x, self.stem, stride=2, pad=3, act=ACT_RELU)
+        N, H, W, _ = images.shape
+        OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
+        Hp, Wp = max(H + 6, 2 * OH + 5), (max(W + 6, 2 * OW + 6) + 1) // 2 * 2
+        x = ops.pack_rgb4_padded(images, self.dtype, 3, 3, Hp, Wp).view(N, Hp, Wp // 2, 8)
+        x, _, _ = ops.conv2d_nhwc(x, self.stem, stride=(2, 1), pad=0, act=ACT_RELU, out_hw=(OH, OW))
         x = ops.maxpool3x3s2(x)
         feats = []
         for blocks in self.levels:
@@ -142,6 +152,7 @@ class CrossAttnPlan:
         self.q = PackedConv(*fold_ln_linear(m.to_q[0], m.to_q[1]), device, dtype)
         wk, bk = fold_ln_linear(m.to_k[0], m.to_k[1])
         wv, bv = fold_ln_linear(m.to_v[0], m.to_v[1])
+        self.wk, self.bk, self.wv, self.bv = wk, bk, wv, bv      # kept for the fused two-attention projection
         self.k = PackedConv(wk, bk, device, dtype)
         self.v = PackedConv(wv, bv, device, dtype)
         # a zero-padded key/value row becomes Linear(LayerNorm(0)) = W beta + b (quirk Q2)
@@ -175,6 +186,9 @@ class FaxStagePlan:
             self.world = _dev_f32(world.reshape(2, -1), device)
         self.a1 = CrossAttnPlan(cva.cross_win_attend_1, device, dtype)
         self.a2 = CrossAttnPlan(cva.cross_win_attend_2, device, dtype)
+        # both attentions project the same normalised key / value maps: one N=256 GEMM each
+        self.k12 = PackedConv(torch.cat([self.a1.wk, self.a2.wk], 0), torch.cat([self.a1.bk, self.a2.bk], 0), device, dtype)
+        self.v12 = PackedConv(torch.cat([self.a1.wv, self.a2.wv], 0), torch.cat([self.a1.bv, self.a2.bv], 0), device, dtype)
         self.m1a = PackedConv(*fold_ln_linear(cva.prenorm_1, cva.mlp_1[0]), device, dtype)
         self.m1b = PackedConv(cva.mlp_1[2].weight.detach().float(), cva.mlp_1[2].bias.detach().float(), device, dtype)
         self.m2a = PackedConv(*fold_ln_linear(cva.prenorm_2, cva.mlp_2[0]), device, dtype)
@@ -202,9 +216,10 @@ class FaxStagePlan:
         else:
             _, _, k_hat = ops.conv2d_nhwc(fa, self.f_proj, res=img, want16=False, ln_out=True)
         _, _, v_hat = ops.conv2d_nhwc(fb, self.f_lin, want16=False, ln_out=True)
-        kv = lambda pc, t: ops.conv2d_nhwc(t, pc)[0].view(BL, n, h, w, d)
-        k1, v1 = kv(self.a1.k, k_hat), kv(self.a1.v, v_hat)
-        k2, v2 = kv(self.a2.k, k_hat), kv(self.a2.v, v_hat)
+        k12 = ops.conv2d_nhwc(k_hat, self.k12)[0].view(BL, n, h, w, 2 * d)
+        v12 = ops.conv2d_nhwc(v_hat, self.v12)[0].view(BL, n, h, w, 2 * d)
+        k1, k2 = k12[..., :d], k12[..., d:]            # column slices: token stride 2d, no copies
+        v1, v2 = v12[..., :d], v12[..., d:]
         fh, fw = self.feat_win
         hp = h if h % fh == 0 else ((h + fh) // fh) * fh                   # pad_divisble, :315-321
         wp = w if w % fw == 0 else ((w + fw) // fw) * fw

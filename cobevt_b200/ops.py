@@ -133,7 +133,7 @@ def _pair(v):
 
 def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=None,
                 out32=False, want16=True, ln_out=False, ln_gamma=None, ln_beta=None,
-                in_upsample=False, ln_eps=1e-5, res_rows=0):
+                in_upsample=False, ln_eps=1e-5, res_rows=0, out_hw=None):
     """x: (N, H, W, Cin) 16-bit contiguous.  Returns (y16 | None, y32 | None, y_ln | None)."""
     assert x.is_cuda and x.is_contiguous() and x.dim() == 4
     N, H, W, Cin = x.shape
@@ -142,6 +142,9 @@ def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=
     (sh, sw), (ph, pw) = _pair(stride), _pair(pad)
     OH = (Hl + 2 * ph - pc.kh) // sh + 1
     OW = (Wl + 2 * pw - pc.kw_logical) // sw + 1
+    if out_hw is not None:           # caller-chosen output window (must lie inside the computed one)
+        assert out_hw[0] <= OH and out_hw[1] <= OW
+        OH, OW = out_hw
     M = N * OH * OW
     y = out if out is not None else (torch.empty((N, OH, OW, pc.cout), dtype=x.dtype, device=x.device) if want16 else None)
     y32 = torch.empty((N, OH, OW, pc.cout), dtype=torch.float32, device=x.device) if out32 else None
@@ -244,6 +247,17 @@ def pack_rgb8(x, dtype):
     npix = x.numel() // 3
     with _timed("eltwise", 0, "pack_rgb8"):
         _lib.check(_lib.lib().cobevt_pack_rgb8(_ptr(x), _ptr(y), npix, dtype_code(dtype), _stream()), "cobevt_pack_rgb8")
+    return y
+
+
+def pack_rgb4_padded(x, dtype, pad_top, pad_left, Hp, Wp):
+    """x (N, H, W, 3) fp32 -> (N, Hp, Wp, 4) 16-bit, zero border."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3
+    N, H, W, _ = x.shape
+    y = torch.empty(N, Hp, Wp, 4, dtype=dtype, device=x.device)
+    with _timed("eltwise", 0, "pack_rgb4_padded"):
+        _lib.check(_lib.lib().cobevt_pack_rgb4_padded(_ptr(x), _ptr(y), N, H, W, Hp, Wp, pad_top, pad_left,
+                                                      dtype_code(dtype), _stream()), "cobevt_pack_rgb4_padded")
     return y
 
 

@@ -122,6 +122,10 @@ int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
 /* (npix,3) fp32 RGB -> (npix,8) 16-bit, channels 3..7 zero.  Replaces the
  * .permute(0,3,1,2).contiguous() copy of resnet_ms.py:62-65 (the stem reads NHWC8). */
 int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t dtype, void* stream);
+/* (N,H,W,3) fp32 RGB -> (N,Hp,Wp,4) 16-bit, image placed at (pad_top, pad_left), zeros elsewhere:
+ * input staging of the 7x7/s2 stem (resnet_ms.py:62-67) -- no bounds checks, 16-byte aligned taps */
+int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                            int32_t pad_top, int32_t pad_left, int32_t dtype, void* stream);
 /* torchvision resnet maxpool (3x3, stride 2, pad 1) on NHWC, resnet_ms.py:71 */
 int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
                              int32_t dtype, void* stream);
