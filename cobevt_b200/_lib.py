@@ -79,7 +79,10 @@ def lib():
 c_i64 = ctypes.c_int64
 _ELTWISE_SIGS = {
     "cobevt_pack_rgb8": [c_vp, c_vp, c_i64, c_i32, c_vp],
-    "cobevt_pack_rgb4_padded": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_pack_rgb4_padded": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp],
+    "cobevt_upsample_bilinear2x": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_add_nearest_relu": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_invert_matrices": [c_vp, c_vp, c_i32, c_i32, c_vp],
     "cobevt_maxpool3x3s2_nhwc": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
     "cobevt_bn_relu2": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "cobevt_ray_embed": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_i32, c_vp],

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
   }
   for (int i = tid; i < 512; i += NUM_THREADS) sBias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   if (tid < 128) {
-    sGamma[tid] = p.ln_gamma ? p.ln_gamma[tid] : 1.f;
-    sBeta[tid] = p.ln_beta ? p.ln_beta[tid] : 0.f;
+    sGamma[tid] = (p.ln_gamma && tid < p.Cout) ? p.ln_gamma[tid] : 1.f;
+    sBeta[tid] = (p.ln_beta && tid < p.Cout) ? p.ln_beta[tid] : 0.f;
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -441,9 +441,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             }
           }
         }
-        if constexpr (BN == 128) {
+        if constexpr (BN == 32 || BN == 64 || BN == 128) {
           if (do_ln) {
-            // exact two-pass statistics on this half (64 values in registers), then combine the halves
+            // exact two-pass statistics on this warp's U columns (in registers); for BN >= 64 the two
+            // column halves combine (mean, M2) through shared memory (Chan et al.)
             float s1 = 0.f;
 #pragma unroll
             for (int j = 0; j < U; ++j) s1 += v[j];
@@ -451,13 +452,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             float m2 = 0.f;
 #pragma unroll
             for (int j = 0; j < U; ++j) { const float d = v[j] - mh; m2 += d * d; }
-            const int par = acc_it & 1;   // exchange slots are double-buffered independently of NACC
-            sXch[par][hf][row] = make_float2(mh, m2);
-            asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory");
-            const float2 o = sXch[par][hf ^ 1][row];
-            const float mean = 0.5f * (mh + o.x);
-            const float dlt = mh - o.x;
-            const float var = (m2 + o.y + dlt * dlt * (float)(U / 2)) * (1.0f / (2 * U));
+            float mean = mh, var = m2 * (1.0f / U);
+            if constexpr (BN >= 64) {
+              const int par = acc_it & 1;   // exchange slots are double-buffered independently of NACC
+              sXch[par][hf][row] = make_float2(mh, m2);
+              asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory");
+              const float2 o = sXch[par][hf ^ 1][row];
+              mean = 0.5f * (mh + o.x);
+              const float dlt = mh - o.x;
+              var = (m2 + o.y + dlt * dlt * (float)(U / 2)) * (1.0f / (2 * U));
+            }
             const float rstd = rsqrtf(var + p.ln_eps);
             if (live) {
               uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
@@ -666,8 +670,8 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
     return cobevt::fail(COBEVT_ERR_SHAPE, "conv: bad extents");
   if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: dtype %d", p->dtype);
   if (!p->y && !p->y32 && !p->y_ln) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: no output");
-  if (p->y_ln && !(p->Cout == 128 && p->block_n == 128))
-    return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: y_ln needs Cout == block_n == 128");
+  if (p->y_ln && !(p->Cout == p->block_n && (p->Cout == 32 || p->Cout == 64 || p->Cout == 128)))
+    return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: y_ln needs Cout == block_n in {32, 64, 128}");
   if ((p->ln_gamma == nullptr) != (p->ln_beta == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "conv: ln_gamma/ln_beta must come together");
   if (p->Cout > 512) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %d > 512", p->Cout);
   if (p->Cout % 8 != 0 && (p->res || p->y_ln)) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: Cout %% 8 with res/ln");

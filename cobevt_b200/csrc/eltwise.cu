@@ -52,10 +52,12 @@ __device__ __forceinline__ void load_row(const uint16_t* row, int C, int lane, i
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     float2 a = up2(u.x, bf16), b = up2(u.y, bf16), c = up2(u.z, bf16), d = up2(u.w, bf16);
     v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y; v[4] = c.x; v[5] = c.y; v[6] = d.x; v[7] = d.y;
-  } else {
+  } else if (per == 2) {
     const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
     float2 a = up2(u, bf16);
     v[0] = a.x; v[1] = a.y;
+  } else {
+    v[0] = up1(*p, bf16);
   }
 }
 __device__ __forceinline__ void store_row(uint16_t* row, int C, int lane, int bf16, const float* v) {
@@ -67,8 +69,10 @@ __device__ __forceinline__ void store_row(uint16_t* row, int C, int lane, int bf
   } else if (per == 8) {
     uint4 u; u.x = pk2(v[0], v[1], bf16); u.y = pk2(v[2], v[3], bf16); u.z = pk2(v[4], v[5], bf16); u.w = pk2(v[6], v[7], bf16);
     *reinterpret_cast<uint4*>(p) = u;
-  } else {
+  } else if (per == 2) {
     *reinterpret_cast<uint32_t*>(p) = pk2(v[0], v[1], bf16);
+  } else {
+    *p = pk1(v[0], bf16);
   }
 }
 
@@ -101,7 +105,7 @@ __global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restri
 // (N,H,W,3) fp32 -> (N, H+pt+pb, Wp, 4) 16-bit with a zero border (pt rows on top, pl columns on the
 // left): the 7x7/s2 stem then needs no bounds checks and its taps start on 16-byte boundaries.
 __global__ void pack_rgb4_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
-                                     int Hp, int Wp, int pt, int pl, int bf16) {
+                                     int Hp, int Wp, int pt, int pl, int nchw, float3 mean, float3 istd, int bf16) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * Hp * Wp) return;
   const int xp = (int)(i % Wp);
@@ -110,9 +114,16 @@ __global__ void pack_rgb4_pad_kernel(const float* __restrict__ x, uint16_t* __re
   const int ys = yp - pt, xs = xp - pl;
   uint2 u = make_uint2(0u, 0u);
   if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
-    const float* s = x + (((int64_t)n * H + ys) * W + xs) * 3;
-    u.x = pk2(s[0], s[1], bf16);
-    u.y = pk2(s[2], 0.f, bf16);
+    float r, g, b;
+    if (nchw) {     // (N,3,H,W) planes (nuScenes batch['image'])
+      const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)ys * W + xs;
+      r = x[o]; g = x[o + hw]; b = x[o + 2 * hw];
+    } else {
+      const float* s = x + (((int64_t)n * H + ys) * W + xs) * 3;
+      r = s[0]; g = s[1]; b = s[2];
+    }
+    u.x = pk2((r - mean.x) * istd.x, (g - mean.y) * istd.y, bf16);
+    u.y = pk2((b - mean.z) * istd.z, 0.f, bf16);
   }
   *reinterpret_cast<uint2*>(y + i * 4) = u;
 }
@@ -435,6 +446,115 @@ __global__ void sttf_kernel(const uint16_t* __restrict__ x, const float* __restr
   if (lane == 0) mask[(((int64_t)b * H + h) * W + w) * L + l] = mk;
 }
 
+
+// ------------------------------------------------------------------ bilinear x2 upsample (align_corners=True)
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True), nuscenes decoder.py:13
+__global__ void upsample_bilinear2x_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
+                                           int C, int bf16) {
+  const int cg = C / 8, OH = 2 * H, OW = 2 * W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * OH * OW * cg) return;
+  const int c8 = (int)(idx % cg);
+  int64_t t = idx / cg;
+  const int ox = (int)(t % OW); t /= OW;
+  const int oy = (int)(t % OH);
+  const int n = (int)(t / OH);
+  const float sy = OH > 1 ? (float)oy * (float)(H - 1) / (float)(OH - 1) : 0.f;
+  const float sx = OW > 1 ? (float)ox * (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const int y0 = (int)sy, x0 = (int)sx;
+  const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+  const float fy = sy - (float)y0, fx = sx - (float)x0;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+  const float wy[2] = {1.f - fy, fy}, wx[2] = {1.f - fx, fx};
+#pragma unroll
+  for (int a = 0; a < 2; ++a)
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + ys[a]) * W + xs[b]) * C + c8 * 8);
+      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+      const float wgt = wy[a] * wx[b];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = up2(w4[j], bf16);
+        acc[2 * j] = fmaf(f.x, wgt, acc[2 * j]);
+        acc[2 * j + 1] = fmaf(f.y, wgt, acc[2 * j + 1]);
+      }
+    }
+  uint4 o;
+  o.x = pk2(acc[0], acc[1], bf16); o.y = pk2(acc[2], acc[3], bf16); o.z = pk2(acc[4], acc[5], bf16); o.w = pk2(acc[6], acc[7], bf16);
+  *reinterpret_cast<uint4*>(y + idx * 8) = o;
+}
+
+// ------------------------------------------------------------------ y = relu(y + nearest_resize(up))
+// DecoderBlock.forward, nuscenes decoder.py:28-36 (F.interpolate default = nearest)
+__global__ void add_nearest_relu_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ up, int N, int H, int W,
+                                        int h, int w, int C, int bf16) {
+  const int cg = C / 8;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * H * W * cg) return;
+  const int c8 = (int)(idx % cg);
+  int64_t t = idx / cg;
+  const int ox = (int)(t % W); t /= W;
+  const int oy = (int)(t % H);
+  const int n = (int)(t / H);
+  // torch nearest: src = floor(dst * (in / out))
+  const int sy = min((int)floorf((float)oy * ((float)h / (float)H)), h - 1);
+  const int sx = min((int)floorf((float)ox * ((float)w / (float)W)), w - 1);
+  const uint4 a = *reinterpret_cast<const uint4*>(y + idx * 8);
+  const uint4 b = *reinterpret_cast<const uint4*>(up + (((int64_t)n * h + sy) * w + sx) * C + c8 * 8);
+  const uint32_t a4[4] = {a.x, a.y, a.z, a.w}, b4[4] = {b.x, b.y, b.z, b.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 fa = up2(a4[j], bf16), fb = up2(b4[j], bf16);
+    o[j] = pk2(fmaxf(fa.x + fb.x, 0.f), fmaxf(fa.y + fb.y, 0.f), bf16);
+  }
+  *reinterpret_cast<uint4*>(y + idx * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------ batched small-matrix inverse (3x3 / 4x4)
+// batch['intrinsics'].inverse(), batch['extrinsics'].inverse()  (encoder_pyramid_axial.py:538-539)
+template <int D>
+__global__ void invert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[D][2 * D];
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) { a[r][c] = src[i * D * D + r * D + c]; a[r][D + c] = (r == c) ? 1.f : 0.f; }
+#pragma unroll
+  for (int col = 0; col < D; ++col) {          // Gauss-Jordan with partial pivoting
+    int piv = col;
+    float best = fabsf(a[col][col]);
+#pragma unroll
+    for (int r = 0; r < D; ++r) if (r > col && fabsf(a[r][col]) > best) { best = fabsf(a[r][col]); piv = r; }
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+      if (r == piv && piv != col) {
+#pragma unroll
+        for (int c = 0; c < 2 * D; ++c) { const float t = a[col][c]; a[col][c] = a[r][c]; a[r][c] = t; }
+      }
+    const float inv = 1.0f / a[col][col];
+#pragma unroll
+    for (int c = 0; c < 2 * D; ++c) a[col][c] *= inv;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+      if (r != col) {
+        const float f = a[r][col];
+#pragma unroll
+        for (int c = 0; c < 2 * D; ++c) a[r][c] = fmaf(-f, a[col][c], a[r][c]);
+      }
+  }
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) dst[i * D * D + r * D + c] = a[r][D + c];
+}
+
 // ------------------------------------------------------------------ layout converters (API boundary)
 // dtype codes: 0 f16, 1 bf16, 2 f32
 __device__ __forceinline__ float ld_any(const void* p, int64_t i, int dt) {
@@ -470,7 +590,7 @@ __global__ void permute_kernel(const void* __restrict__ src, void* __restrict__ 
 }
 
 inline unsigned blocks_for(int64_t threads, int bs) { return (unsigned)((threads + bs - 1) / bs); }
-inline bool ok_c(int C) { return C == 64 || C == 128 || C == 256; }
+inline bool ok_c(int C) { return C == 32 || C == 64 || C == 128 || C == 256; }
 
 }  // namespace
 
@@ -484,10 +604,14 @@ extern "C" int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t d
 }
 
 extern "C" int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
-                                        int32_t pad_top, int32_t pad_left, int32_t dtype, void* stream) {
+                                        int32_t pad_top, int32_t pad_left, int32_t src_nchw, const float* mean3,
+                                        const float* std3, int32_t dtype, void* stream) {
   if (!x || !y || N <= 0 || Hp < H + pad_top || Wp < W + pad_left) return fail(COBEVT_ERR_SHAPE, "pack_rgb4_padded: bad args");
   const int64_t total = (int64_t)N * Hp * Wp;
-  pack_rgb4_pad_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, dtype);
+  // mean3 / std3 are HOST pointers (3 floats each) or NULL: the Normalize of encoder_pyramid_axial.py:41-49
+  float3 mean = make_float3(0.f, 0.f, 0.f), istd = make_float3(1.f, 1.f, 1.f);
+  if (mean3 && std3) { mean = make_float3(mean3[0], mean3[1], mean3[2]); istd = make_float3(1.f / std3[0], 1.f / std3[1], 1.f / std3[2]); }
+  pack_rgb4_pad_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, src_nchw, mean, istd, dtype);
   return cobevt::check_launch("pack_rgb4_padded");
 }
 
@@ -514,6 +638,7 @@ extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const fl
   if (!I_inv || !E_inv || !w_img || !w_cam || !out || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "ray_embed: bad args (C must be 64/128/256)");
   dim3 grid((h * w + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, NV);
   if (C == 128) ray_embed_kernel<4><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else if (C == 32) ray_embed_kernel<1><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   else if (C == 64) ray_embed_kernel<2><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   else ray_embed_kernel<8><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   return cobevt::check_launch("ray_embed");
@@ -526,6 +651,7 @@ extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* worl
     return fail(COBEVT_ERR_SHAPE, "bev_query: bad args");
   dim3 grid((P + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, BL * n);
   if (C == 128) bev_query_kernel<4><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else if (C == 32) bev_query_kernel<1><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   else if (C == 64) bev_query_kernel<2><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   else bev_query_kernel<8><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   return cobevt::check_launch("bev_query");
@@ -554,6 +680,29 @@ extern "C" int cobevt_sttf_regroup(const void* x, const float* tm, const int64_t
   sttf_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, tm, record_len, (uint16_t*)out, mask, B, L, H,
                                                                 W, C, inv_disc, use_roi_mask, dtype);
   return cobevt::check_launch("sttf");
+}
+
+extern "C" int cobevt_upsample_bilinear2x(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype,
+                                           void* stream) {
+  if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "upsample_bilinear2x: bad args");
+  const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
+  upsample_bilinear2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, dtype);
+  return cobevt::check_launch("upsample_bilinear2x");
+}
+
+extern "C" int cobevt_add_nearest_relu(void* y, const void* up, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w,
+                                        int32_t C, int32_t dtype, void* stream) {
+  if (!y || !up || C % 8) return fail(COBEVT_ERR_SHAPE, "add_nearest_relu: bad args");
+  const int64_t total = (int64_t)N * H * W * (C / 8);
+  add_nearest_relu_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((uint16_t*)y, (const uint16_t*)up, N, H, W, h, w, C, dtype);
+  return cobevt::check_launch("add_nearest_relu");
+}
+
+extern "C" int cobevt_invert_matrices(const float* src, float* dst, int32_t n, int32_t dim, void* stream) {
+  if (!src || !dst || n <= 0 || (dim != 3 && dim != 4)) return fail(COBEVT_ERR_SHAPE, "invert_matrices: dim must be 3 or 4");
+  if (dim == 3) invert_kernel<3><<<blocks_for(n, 128), 128, 0, ST(stream)>>>(src, dst, n);
+  else invert_kernel<4><<<blocks_for(n, 128), 128, 0, ST(stream)>>>(src, dst, n);
+  return cobevt::check_launch("invert_matrices");
 }
 
 extern "C" int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cpad,

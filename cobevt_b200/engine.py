@@ -84,12 +84,15 @@ class ResNetPlan:
                 blocks.append((convs, ds))
             self.levels.append(blocks)
 
-    def run(self, images):
-        """images (NI, H, W, 3) fp32 -> list of NHWC 16-bit feature maps, one per level."""
-        N, H, W, _ = images.shape
+    def run(self, images, nchw=False, mean=None, std=None):
+        """images (NI, H, W, 3) [or (NI, 3, H, W) with nchw] fp32 -> list of NHWC 16-bit feature maps."""
+        if nchw:
+            N, _, H, W = images.shape
+        else:
+            N, H, W, _ = images.shape
         OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         Hp, Wp = max(H + 6, 2 * OH + 5), (max(W + 6, 2 * OW + 6) + 1) // 2 * 2
-        x = ops.pack_rgb4_padded(images, self.dtype, 3, 3, Hp, Wp).view(N, Hp, Wp // 2, 8)
+        x = ops.pack_rgb4_padded(images, self.dtype, 3, 3, Hp, Wp, nchw=nchw, mean=mean, std=std).view(N, Hp, Wp // 2, 8)
         x, _, _ = ops.conv2d_nhwc(x, self.stem, stride=(2, 1), pad=0, act=ACT_RELU, out_hw=(OH, OW))
         x = ops.maxpool3x3s2(x)
         feats = []
@@ -281,7 +284,8 @@ class FaxPlan:
                        for i, cv in enumerate(fax.cross_views)]
         self.layers = [[BottleneckPlan(b, device, dtype) for b in seq] for seq in fax.layers]
         self.down = [DownsamplePlan(seq[0], device, dtype) for seq in fax.downsample_layers]
-        self.self_attn = GlobalAttnPlan(fax.self_attn, device, dtype) if fax.self_attn is not None else None
+        sa = getattr(fax, 'self_attn', None)
+        self.self_attn = GlobalAttnPlan(sa, device, dtype) if sa is not None else None
         prior = be.learned_features.detach().float().permute(1, 2, 0).contiguous()         # H W d
         self.prior = prior.to(dtype).to(device)[None]
 
@@ -390,3 +394,77 @@ class SegHeadPlan:
         if "static_seg" not in out:
             out["static_seg"] = torch.zeros_like(out["dynamic_seg"])
         return out
+
+
+# --------------------------------------------------------------------------- nuScenes SinBEVT (CVT fork)
+class PyramidPlan:
+    """PyramidAxialEncoder (nuscenes/cross_view_transformer/model/encoder_pyramid_axial.py:475-558):
+    the same FAX stages / Bottlenecks / downsample blocks with per-stage widths (32/64/128, heads
+    1/2/4), no global self-attention, intrinsics AND extrinsics inverted (:538-539)."""
+
+    def __init__(self, enc, device, dtype):
+        self.dtype = dtype
+        be = enc.bev_embedding
+        self.stages = [FaxStagePlan(cv, getattr(be, f"grid{i}")[:2], device, dtype) for i, cv in enumerate(enc.cross_views)]
+        self.layers = [[BottleneckPlan(b, device, dtype) for b in seq] for seq in enc.layers]
+        self.down = [DownsamplePlan(seq[0], device, dtype) for seq in enc.downsample_layers]
+        prior = be.learned_features.detach().float().permute(1, 2, 0).contiguous()
+        self.prior = prior.to(dtype).to(device)[None]
+
+    def run(self, feats, n, intrinsics, extrinsics):
+        """feats: list of (b*n, h, w, Cf) NHWC; intrinsics (b*n,3,3), extrinsics (b*n,4,4) fp32 (not inverted)."""
+        b = feats[0].shape[0] // n
+        E_inv = ops.invert_matrices(extrinsics)
+        I_inv = ops.invert_matrices(intrinsics)
+        x, x_ln, x_rows = self.prior, None, 1
+        for i, st in enumerate(self.stages):
+            x = st.run(x, x_ln, x_rows, feats[i], n, I_inv, E_inv, invert_intrinsic=False)
+            x_rows = b
+            for blk in self.layers[i]:
+                x = blk.run(x)
+            x_ln = None
+            if i < len(self.stages) - 1:
+                x, _, x_ln = self.down[i].run(x, not self.stages[i + 1].bev_flag)
+        return x
+
+
+class CvtDecoderPlan:
+    """Decoder / DecoderBlock (nuscenes/.../model/decoder.py:6-61)."""
+
+    def __init__(self, dec, device, dtype):
+        self.blocks = []
+        for blk in dec.layers:
+            conv = blk.conv
+            a = PackedConv(*fold_conv_bn(conv[1], conv[2]), device, dtype)
+            b = PackedConv(*fold_conv_bn(conv[4], conv[5]), device, dtype)
+            up = None
+            if blk.up is not None:
+                up = PackedConv(blk.up.weight.detach().float(), blk.up.bias.detach().float(), device, dtype)
+            self.blocks.append((a, b, up))
+
+    def run(self, x):
+        skip = x
+        y = x
+        for a, b, up in self.blocks:
+            y = ops.upsample_bilinear2x(y)
+            y, _, _ = ops.conv2d_nhwc(y, a, pad=1, act=ACT_RELU)
+            if up is None:
+                y, _, _ = ops.conv2d_nhwc(y, b, act=ACT_RELU)
+            else:
+                y, _, _ = ops.conv2d_nhwc(y, b)
+                u, _, _ = ops.conv2d_nhwc(skip, up)
+                ops.add_nearest_relu_(y, u)
+        return y
+
+
+class LogitsPlan:
+    """to_logits of CrossViewTransformer (nuscenes/.../model/cvt.py:29-33)."""
+
+    def __init__(self, seq, device, dtype):
+        self.a = PackedConv(*fold_conv_bn(seq[0], seq[1]), device, dtype)
+        self.b = PackedConv(seq[3].weight.detach().float(), seq[3].bias.detach().float(), device, dtype)
+
+    def run(self, y):
+        y, _, _ = ops.conv2d_nhwc(y, self.a, pad=1, act=ACT_RELU)
+        _, z32, _ = ops.conv2d_nhwc(y, self.b, want16=False, out32=True)
+        return ops.nhwc_to_nchw(z32, torch.float32)

@@ -250,15 +250,56 @@ def pack_rgb8(x, dtype):
     return y
 
 
-def pack_rgb4_padded(x, dtype, pad_top, pad_left, Hp, Wp):
-    """x (N, H, W, 3) fp32 -> (N, Hp, Wp, 4) 16-bit, zero border."""
-    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[-1] == 3
-    N, H, W, _ = x.shape
+def pack_rgb4_padded(x, dtype, pad_top, pad_left, Hp, Wp, nchw=False, mean=None, std=None):
+    """x (N, H, W, 3) [or (N, 3, H, W) with nchw=True] fp32 -> (N, Hp, Wp, 4) 16-bit, zero border;
+    optional per-channel (x - mean) / std (host triples)."""
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    if nchw:
+        N, _, H, W = x.shape
+        assert x.shape[1] == 3
+    else:
+        N, H, W, _ = x.shape
+        assert x.shape[-1] == 3
     y = torch.empty(N, Hp, Wp, 4, dtype=dtype, device=x.device)
+    m3 = s3 = None
+    if mean is not None:
+        m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
     with _timed("eltwise", 0, "pack_rgb4_padded"):
         _lib.check(_lib.lib().cobevt_pack_rgb4_padded(_ptr(x), _ptr(y), N, H, W, Hp, Wp, pad_top, pad_left,
-                                                      dtype_code(dtype), _stream()), "cobevt_pack_rgb4_padded")
+                                                      1 if nchw else 0, m3, s3, dtype_code(dtype), _stream()),
+                   "cobevt_pack_rgb4_padded")
     return y
+
+
+def upsample_bilinear2x(x):
+    N, H, W, C = x.shape
+    y = torch.empty(N, 2 * H, 2 * W, C, dtype=x.dtype, device=x.device)
+    with _timed("eltwise", 0, "upsample_bilinear2x"):
+        _lib.check(_lib.lib().cobevt_upsample_bilinear2x(_ptr(x), _ptr(y), N, H, W, C, dtype_code(x.dtype), _stream()),
+                   "cobevt_upsample_bilinear2x")
+    return y
+
+
+def add_nearest_relu_(y, up):
+    """y (N,H,W,C) <- relu(y + nearest_resize(up (N,h,w,C)))  in place."""
+    N, H, W, C = y.shape
+    _, h, w, _ = up.shape
+    with _timed("eltwise", 0, "add_nearest_relu"):
+        _lib.check(_lib.lib().cobevt_add_nearest_relu(_ptr(y), _ptr(up), N, H, W, h, w, C, dtype_code(y.dtype), _stream()),
+                   "cobevt_add_nearest_relu")
+    return y
+
+
+def invert_matrices(m):
+    """(..., d, d) fp32 with d in {3, 4} -> inverse."""
+    m = m.float().contiguous()
+    d = m.shape[-1]
+    out = torch.empty_like(m)
+    with _timed("eltwise", 0, "invert_matrices"):
+        _lib.check(_lib.lib().cobevt_invert_matrices(_ptr(m), _ptr(out), m.numel() // (d * d), d, _stream()),
+                   "cobevt_invert_matrices")
+    return out
 
 
 def maxpool3x3s2(x):

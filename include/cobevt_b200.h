@@ -54,7 +54,7 @@ typedef struct {
   void* y;             /* (M, Cout) 16-bit output or NULL                             */
   float* y32;          /* (M, Cout) fp32 output or NULL                               */
   void* y_ln;          /* (M, Cout) 16-bit LayerNorm of the output row, or NULL; requires
-                          Cout == block_n == 128                                      */
+                          Cout == block_n in {32, 64, 128}                            */
   const float* ln_gamma; /* [Cout] affine of y_ln, or NULL for the plain normalised row
                           (consumers fold their own LayerNorm affine into their weights) */
   const float* ln_beta;
@@ -125,7 +125,17 @@ int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t dtype, void*
 /* (N,H,W,3) fp32 RGB -> (N,Hp,Wp,4) 16-bit, image placed at (pad_top, pad_left), zeros elsewhere:
  * input staging of the 7x7/s2 stem (resnet_ms.py:62-67) -- no bounds checks, 16-byte aligned taps */
 int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
-                            int32_t pad_top, int32_t pad_left, int32_t dtype, void* stream);
+                            int32_t pad_top, int32_t pad_left, int32_t src_nchw, const float* mean3_host,
+                            const float* std3_host, int32_t dtype, void* stream);
+/* nn.Upsample(x2, bilinear, align_corners=True) on NHWC 16-bit; nuscenes .../decoder.py:13 */
+int cobevt_upsample_bilinear2x(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t dtype,
+                               void* stream);
+/* y = relu(y + nearest_resize(up -> HxW)) in place: DecoderBlock.forward, nuscenes .../decoder.py:28-36 */
+int cobevt_add_nearest_relu(void* y, const void* up, int32_t N, int32_t H, int32_t W, int32_t h, int32_t w,
+                            int32_t C, int32_t dtype, void* stream);
+/* batched fp32 3x3 / 4x4 inverse (Gauss-Jordan, partial pivoting): intrinsics / extrinsics .inverse(),
+ * nuscenes .../encoder_pyramid_axial.py:538-539 */
+int cobevt_invert_matrices(const float* src, float* dst, int32_t n, int32_t dim, void* stream);
 /* torchvision resnet maxpool (3x3, stride 2, pad 1) on NHWC, resnet_ms.py:71 */
 int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C,
                              int32_t dtype, void* stream);

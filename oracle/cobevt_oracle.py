@@ -175,12 +175,13 @@ def cross_view_swap_attention(x, world, feature, I_inv, E_inv, sd, p, *, image_h
     """
     b, n, _, h, w = feature.shape
     d, H, W = x.shape[1:]
-    pix = image_plane(h, w, image_h, image_w).reshape(3, h * w)
+    dev = x.device
+    pix = image_plane(h, w, image_h, image_w).reshape(3, h * w).to(dev)
     # :346-358 camera-centre and ray-direction embeddings
     c = E_inv[..., -1:].reshape(b * n, 4, 1, 1)
     c_embed = _conv(c, sd, p + ".cam_embed")                                   # (bn, d, 1, 1)
     cam = I_inv @ pix                                                           # b n 3 hw
-    cam = torch.cat([cam, torch.ones(b, n, 1, h * w)], 2)
+    cam = torch.cat([cam, torch.ones(b, n, 1, h * w, device=dev)], 2)
     dirs = (E_inv @ cam).reshape(b * n, 4, h, w)
     img_embed = _conv(dirs, sd, p + ".img_embed") - c_embed
     img_embed = img_embed / (img_embed.norm(dim=1, keepdim=True) + 1e-7)
@@ -239,7 +240,7 @@ def global_attention(x, sd, p, dim_head, window_size):
     q, k, v = _lin(t, sd, p + ".to_qkv").chunk(3, -1)
     sh = lambda u: u.reshape(b, H * W, heads, dim_head).permute(0, 2, 1, 3)
     q, k, v = sh(q) * dim_head ** -0.5, sh(k), sh(v)
-    bias = sd[p + ".rel_pos_bias.weight"][rel_pos_index_2d(window_size)]        # T T heads
+    bias = sd[p + ".rel_pos_bias.weight"][rel_pos_index_2d(window_size).to(x.device)]        # T T heads
     sim = q @ k.transpose(-1, -2) + bias.permute(2, 0, 1)
     out = sim.softmax(-1) @ v
     out = out.permute(0, 2, 1, 3).reshape(b, H, W, d)
@@ -263,7 +264,7 @@ def fax_module(features, intrinsic, extrinsic, sd, prefix, cfg):
     for i, feat in enumerate(features):
         f = feat.reshape(b * l, *feat.shape[2:])
         x = cross_view_swap_attention(
-            x, grids[i][:2], f, I_inv, E_inv, sd, f"{prefix}cross_views.{i}",
+            x, grids[i][:2].to(x.device), f, I_inv, E_inv, sd, f"{prefix}cross_views.{i}",
             image_h=cv["image_height"], image_w=cv["image_width"], q_win=sw["q_win_size"][i],
             feat_win=sw["feat_win_size"][i], heads=cv["heads"][i], dim_head=cv["dim_head"][i],
             bev_embed_flag=sw["bev_embedding_flag"][i], no_image_features=cv["no_image_features"],
@@ -302,7 +303,7 @@ def swap_attention(xp, mask_p, sd, p, dim_head, L, ws):
     q, k, v = _lin(xp, sd, p + ".to_qkv").chunk(3, -1)
     sh = lambda u: u.reshape(Bw, T, heads, dim_head).permute(0, 2, 1, 3)
     q, k, v = sh(q) * dim_head ** -0.5, sh(k), sh(v)
-    bias = sd[p + ".relative_position_bias_table.weight"][rel_pos_index_3d(L, ws, ws)]
+    bias = sd[p + ".relative_position_bias_table.weight"][rel_pos_index_3d(L, ws, ws).to(xp.device)]
     sim = q @ k.transpose(-1, -2) + bias.permute(2, 0, 1)
     if mask_p is not None:
         sim = sim.masked_fill(mask_p[:, None, None, :] == 0, float("-inf"))
@@ -368,24 +369,25 @@ def regroup(x, record_len, max_len):
     for n in [int(v) for v in record_len]:
         f = x[s:s + n]
         s += n
-        out.append(torch.cat([f, torch.zeros(max_len - n, *x.shape[1:])], 0))
+        out.append(torch.cat([f, torch.zeros(max_len - n, *x.shape[1:], device=x.device)], 0))
         mask.append([1] * n + [0] * (max_len - n))
-    return torch.stack(out, 0), torch.tensor(mask)
+    return torch.stack(out, 0), torch.tensor(mask, device=x.device)
 
 
 def _sttf_pixel_matrix(tm, resolution, downsample_rate, H, W):
     """The 3x3 pixel-space matrix T (dst <- src) the reference hands to warp_affine:
     torch_transformation_utils.py:108-134 (discretise) and :254-297 (rotate about the centre)."""
     m = tm[..., [0, 1], :][..., [0, 1, 3]].clone().float()                       # (..., 2, 3)
+    dev = tm.device
     m[..., 2] = m[..., 2] / (resolution * downsample_rate)
     m = m.reshape(-1, 2, 3)
     N = m.shape[0]
     cx, cy = W / 2, H / 2
-    sh = torch.eye(3).repeat(N, 1, 1)
+    sh = torch.eye(3, device=dev).repeat(N, 1, 1)
     sh[:, 0, 2], sh[:, 1, 2] = cx, cy
-    shi = torch.eye(3).repeat(N, 1, 1)
+    shi = torch.eye(3, device=dev).repeat(N, 1, 1)
     shi[:, 0, 2], shi[:, 1, 2] = -cx, -cy
-    rot = torch.eye(3).repeat(N, 1, 1)
+    rot = torch.eye(3, device=dev).repeat(N, 1, 1)
     rot[:, :2, :2] = m[:, :, :2]
     T = sh @ rot @ shi
     T[:, :2, 2] += m[:, :, 2]
@@ -398,8 +400,9 @@ def warp_affine_pixels(src, T, mode):
     src at T^-1 (x_dst, y_dst, 1), zeros outside.  src (N, C, H, W), T (N, 3, 3)."""
     N, C, H, W = src.shape
     Ti = T.inverse()
-    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
-    p = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W)], 0)       # 3, HW
+    dev = src.device
+    ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev), torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
+    p = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, device=dev)], 0)       # 3, HW
     s = Ti @ p                                                                    # N 3 HW
     sx, sy = s[:, 0], s[:, 1]
     flat = src.reshape(N, C, H * W)
@@ -433,7 +436,7 @@ def roi_and_cav_mask(shape, cav_mask, tm, resolution, downsample_rate):
     """get_roi_and_cav_mask, torch_transformation_utils.py:11-49 -> (B, H, W, 1, L)."""
     B, L, H, W, _ = shape
     T = _sttf_pixel_matrix(tm, resolution, downsample_rate, H, W)
-    roi = warp_affine_pixels(torch.ones(B * L, 1, H, W), T, "nearest").reshape(B, L, 1, H, W)
+    roi = warp_affine_pixels(torch.ones(B * L, 1, H, W, device=tm.device), T, "nearest").reshape(B, L, 1, H, W)
     com = roi * cav_mask[:, :, None, None, None].float()
     return com.permute(0, 3, 4, 2, 1)
 
@@ -473,7 +476,7 @@ def corpbevt(batch, sd, cfg):
     feats = resnet_encoder(x, sd, "encoder.", enc["num_layers"], enc["id_pick"])
     y = fax_module(feats, batch["intrinsic"], batch["extrinsic"], sd, "fax.", cfg["fax"])
     y = y.squeeze(1)
-    y, mask = regroup(y, batch["record_len"], cfg["max_cav"])
+    y, mask = regroup(y, batch["record_len"].tolist(), cfg["max_cav"])
     st = cfg["sttf"]
     tm = batch["transformation_matrix"]
     y = sttf(y, tm, st["resolution"], st["downsample_rate"])                     # B L H W C
