@@ -60,3 +60,29 @@ def fax_fused_args(cfg):
     """The SinBEVT-only model (fax.yaml / FaxFusedTransformer) from a CoBEVT argument dict."""
     c = copy.deepcopy(cfg)
     return {k: c[k] for k in ('target', 'encoder', 'decoder', 'fax', 'seg_head_dim', 'output_class')}
+
+
+def nuscenes_cvt(image_h=224, image_w=480, bev=200, q_win=((10, 10), (10, 10), (25, 25)),
+                 feat_win=((6, 12), (6, 12), (14, 30))):
+    """nuscenes/config/model/cvt_pyramid_axial.yaml:9-58 as constructor kwargs.  Defaults = the reference's
+    native 200x200 BEV (56x120 / 28x60 features are zero-padded to 60x120 / 30x60: quirk Q2 is live);
+    BASELINE config C2 is `nuscenes_cvt(bev=256, q_win=((16,16),(16,16),(32,32)), feat_win=((7,15),(7,15),(14,30)))`."""
+    return {
+        'encoder': {
+            'dim': [32, 64, 128], 'middle': [2, 2, 2], 'scale': 1.0,
+            'cross_view': {'heads': [1, 2, 4], 'dim_head': [32, 32, 32], 'qkv_bias': True, 'skip': True,
+                           'no_image_features': False, 'image_height': image_h, 'image_width': image_w},
+            'cross_view_swap': {'rel_pos_emb': False, 'q_win_size': [list(w) for w in q_win],
+                                'feat_win_size': [list(w) for w in feat_win],
+                                'bev_embedding_flag': [True, False, False]},
+            'bev_embedding': {'sigma': 1.0, 'bev_height': bev, 'bev_width': bev, 'h_meters': 100.0,
+                              'w_meters': 100.0, 'offset': 0.0, 'upsample_scales': [2, 4, 8]},
+            'self_attn': {'dim_head': 32, 'dropout': 0.1, 'window_size': 25},
+        },
+        'decoder_blocks': [128, 128, 64], 'decoder_dim': 128, 'dim_last': 64,
+        'outputs': {'bev': [0, 1], 'center': [1, 2]},
+    }
+
+
+def nuscenes_c2():
+    return nuscenes_cvt(bev=256, q_win=((16, 16), (16, 16), (32, 32)), feat_win=((7, 15), (7, 15), (14, 30)))

@@ -89,3 +89,23 @@ def synth_batch(cfg, record_len=(5,), n_cams=4, seed=1, fov_deg=100.0):
 
 def to_device(batch, device):
     return {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in batch.items()}
+
+
+def synth_nuscenes_batch(image_h, image_w, b=1, n_cams=6, seed=1, fov_deg=70.0):
+    """nuScenes-style batch: image (b,n,3,H,W) in [0,1); intrinsics (b,n,3,3); extrinsics (b,n,4,4) =
+    ego->camera rigid transforms (the model inverts them, encoder_pyramid_axial.py:539)."""
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand(b, n_cams, 3, image_h, image_w, generator=g)
+    f = image_w / (2 * math.tan(math.radians(fov_deg) / 2))
+    K = torch.tensor([[f, 0., image_w / 2], [0., f, image_h / 2], [0., 0., 1.]])
+    intr = K.expand(b, n_cams, 3, 3).clone() * (1 + 0.01 * torch.randn(b, n_cams, 3, 3, generator=g))
+    intr[..., 2, :] = torch.tensor([0., 0., 1.])
+    cam2ego = torch.tensor([[0., 0., 1.], [-1., 0., 0.], [0., -1., 0.]])
+    extr = torch.zeros(b, n_cams, 4, 4)
+    for i in range(b):
+        for k in range(n_cams):
+            T = torch.eye(4)
+            T[:3, :3] = _rot_z(2 * math.pi * k / n_cams) @ cam2ego
+            T[:3, 3] = (torch.rand(3, generator=g) - 0.5) * 3.0
+            extr[i, k] = torch.linalg.inv(T)
+    return {'image': image, 'intrinsics': intr, 'extrinsics': extr}

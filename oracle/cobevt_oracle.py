@@ -500,3 +500,75 @@ def fax_fused_transformer(batch, sd, cfg):
     y = naive_decoder(y, sd, "decoder.", cfg["decoder"]["num_layer"])
     y = y.reshape(b * l, *y.shape[2:])
     return bev_seg_head(y, sd, "seg_head.", cfg["target"], b, l)
+
+
+# --------------------------------------------------------------------------- nuScenes SinBEVT (CVT fork)
+def pyramid_axial_encoder(features, intrinsics, extrinsics, sd, prefix, cfg):
+    """PyramidAxialEncoder.forward after the backbone, nuscenes/.../encoder_pyramid_axial.py:534-558.
+
+    features: list of (b*n, c, h, w); intrinsics (b, n, 3, 3), extrinsics (b, n, 4, 4) -- BOTH inverted
+    here (:538-539).  cfg: the constructor kwargs (cross_view, cross_view_swap, bev_embedding, dim, middle).
+    """
+    b, n = intrinsics.shape[:2]
+    I_inv, E_inv = intrinsics.inverse(), extrinsics.inverse()
+    be = cfg["bev_embedding"]
+    grids = bev_world_grids(be["bev_height"], be["bev_width"], be["h_meters"], be["w_meters"], be["offset"],
+                            be["upsample_scales"])
+    x = sd[prefix + "bev_embedding.learned_features"][None].expand(b, -1, -1, -1)
+    cv, sw = cfg["cross_view"], cfg["cross_view_swap"]
+    for i, feat in enumerate(features):
+        f = feat.reshape(b, n, *feat.shape[1:])
+        x = cross_view_swap_attention(
+            x, grids[i][:2].to(x.device), f, I_inv, E_inv, sd, f"{prefix}cross_views.{i}",
+            image_h=cv["image_height"], image_w=cv["image_width"], q_win=sw["q_win_size"][i],
+            feat_win=sw["feat_win_size"][i], heads=cv["heads"][i], dim_head=cv["dim_head"][i],
+            bev_embed_flag=sw["bev_embedding_flag"][i], no_image_features=cv["no_image_features"], skip=cv["skip"])
+        for j in range(cfg["middle"][i]):
+            x = bottleneck(x, sd, f"{prefix}layers.{i}.{j}")
+        if i < len(features) - 1:                        # encoder_pyramid_axial.py:513-527 (dim -> dim/2 -> unshuffle)
+            dp = f"{prefix}downsample_layers.{i}.0"
+            x = F.pixel_unshuffle(_conv(x, sd, dp + ".0", 1, 1), 2)
+            x = F.relu(_bn(_conv(x, sd, dp + ".2", 1, 1), sd, dp + ".3"))
+            x = _bn(_conv(x, sd, dp + ".5"), sd, dp + ".6")
+    return x
+
+
+def cvt_decoder(x, sd, prefix, n_blocks):
+    """Decoder.forward, nuscenes/.../decoder.py:55-61 with DecoderBlock.forward :28-36."""
+    y = x
+    for i in range(n_blocks):
+        p = f"{prefix}layers.{i}"
+        t = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+        t = F.relu(_bn(_conv(t, sd, p + ".conv.1", 1, 1), sd, p + ".conv.2"))
+        t = _bn(_conv(t, sd, p + ".conv.4"), sd, p + ".conv.5")
+        if (p + ".up.weight") in sd:
+            up = F.interpolate(_conv(x, sd, p + ".up"), t.shape[-2:])          # nearest
+            t = t + up
+        y = F.relu(t)
+    return y
+
+
+def resnet_levels(image_nchw, sd, prefix, num_layers=34, n_levels=3):
+    """torchvision ResNet levels 1..n on an NCHW image (the backbone adaptor of SURVEY 8d (ii))."""
+    x = F.relu(_bn(_conv(image_nchw, sd, prefix + "conv1", 2, 3), sd, prefix + "bn1"))
+    x = F.max_pool2d(x, 3, 2, 1)
+    feats = []
+    for li, nblk in enumerate(_RESNET_BLOCKS[num_layers][:n_levels]):
+        for bi in range(nblk):
+            x = resnet_basic_block(x, sd, f"{prefix}layer{li + 1}.{bi}", 2 if (li > 0 and bi == 0) else 1)
+        feats.append(x)
+    return feats
+
+
+def cross_view_transformer(batch, sd, cfg, backbone_fn):
+    """CrossViewTransformer.forward, nuscenes/.../cvt.py:35-40.  backbone_fn(normalised (b*n,3,H,W)) -> features."""
+    image = batch["image"]
+    b, n = image.shape[:2]
+    mean = torch.tensor([0.485, 0.456, 0.406], device=image.device)[None, :, None, None]
+    std = torch.tensor([0.229, 0.224, 0.225], device=image.device)[None, :, None, None]
+    feats = backbone_fn((image.flatten(0, 1) - mean) / std)
+    x = pyramid_axial_encoder(feats, batch["intrinsics"], batch["extrinsics"], sd, "encoder.", cfg["encoder"])
+    y = cvt_decoder(x, sd, "decoder.", len(cfg["decoder_blocks"]))
+    z = F.relu(_bn(_conv(y, sd, "to_logits.0", 1, 1), sd, "to_logits.1"))
+    z = _conv(z, sd, "to_logits.3")
+    return {k: z[:, a:b_] for k, (a, b_) in cfg["outputs"].items()}

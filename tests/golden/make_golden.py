@@ -32,6 +32,13 @@ CASES = {
 }
 
 
+NUSC_CASES = {
+    # name: (config builder, H, W, n_cams, weight seed, input seed)
+    "cvt_native200_1cam": (lambda: configs.nuscenes_cvt(224, 224, 200, feat_win=((6, 6), (6, 6), (14, 14))), 224, 224, 1, 0, 2),
+    "cvt_c2_bev256_2cam": (configs.nuscenes_c2, 224, 480, 2, 0, 2),
+}
+
+
 def _nomask(cfg):
     cfg["fax_fusion"]["mask"] = False
     return cfg
@@ -57,6 +64,21 @@ def main():
                     "weights_checksum": float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point())),
                     "torch": torch.__version__}, os.path.join(HERE, name + ".pt"))
         print(name, tuple(dyn.shape), float(dyn.abs().max()))
+    import nusc_common as nc
+    nref = refimport.load_nuscenes()
+    for name, (mk, H, W, n_cams, wseed, iseed) in NUSC_CASES.items():
+        cfg = mk()
+        m = nc.build_reference(nref, cfg, H, W)
+        sd = synth.synth_state_dict(m, seed=wseed)
+        m.load_state_dict(sd)
+        batch = synth.synth_nuscenes_batch(H, W, b=1, n_cams=n_cams, seed=iseed)
+        with torch.no_grad():
+            out = m(copy.deepcopy(batch))
+        torch.save({"case": name, "kind": "cvt", "config": cfg, "H": H, "W": W, "n_cams": n_cams,
+                    "weight_seed": wseed, "input_seed": iseed, "outputs": {k: v.clone() for k, v in out.items()},
+                    "weights_checksum": float(sum(v.double().abs().sum() for v in sd.values() if v.is_floating_point())),
+                    "torch": torch.__version__}, os.path.join(HERE, name + ".pt"))
+        print(name, {k: tuple(v.shape) for k, v in out.items()})
 
 
 if __name__ == "__main__":

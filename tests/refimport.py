@@ -29,3 +29,15 @@ def load_opv2v():
     import opencood.models.fusion_modules.swap_fusion_modules as swap
     import opencood.models.backbones.resnet_ms as resnet_ms
     return types.SimpleNamespace(corpbevt=corp, fax_fused=fft, fax=fax, swap=swap, resnet_ms=resnet_ms)
+
+
+def load_nuscenes():
+    """nuscenes/cross_view_transformer model modules (pure torch + einops; no hydra/lightning needed)."""
+    if not os.path.isdir(os.path.join(REF_NUSC, "cross_view_transformer")):
+        raise RuntimeError("reference not present")
+    if REF_NUSC not in sys.path:
+        sys.path.insert(0, REF_NUSC)
+    import cross_view_transformer.model.encoder_pyramid_axial as epa
+    import cross_view_transformer.model.decoder as dec
+    import cross_view_transformer.model.cvt as cvt
+    return types.SimpleNamespace(epa=epa, decoder=dec, cvt=cvt)
