@@ -33,7 +33,7 @@ constexpr int TMEM_COLS = 256;  // S: [0,128)  O: [128,160)
 
 struct AArgs {
   CobevtAttnParams p;
-  int32_t n_win, q_tiles, Lq, Lk, n_chunks, q_passes, C;
+  int32_t n_win, q_tiles, Lq, Lk, n_chunks, q_passes, C, q_dbuf;
   int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
   uint32_t idesc_qk, idesc_pv;
 };
@@ -337,26 +337,41 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
 // =====================================================================================
 constexpr int CH = 64;                                 // keys per chunk
 constexpr int KV_CAP_KEYS = 1024;
-constexpr int V2_THREADS = 320;   // 2 softmax warpgroups + 2 MMA-issuer warps
+constexpr int V2_THREADS = 384;   // 2 softmax warpgroups + 1 warpgroup holding the 2 MMA-issuer warps (8, 9)
+constexpr int V2_REGS_SOFTMAX = 224, V2_REGS_ISSUER = 40;   // setmaxnreg split of the 64K register file
 constexpr int SP2_BYTES = TILE_Q * CH * 2;             // 16 KB per P buffer
-constexpr int V2_FIXED_SMEM = 1024 + 2 * SQ_BYTES + 2 * 2 * SP2_BYTES;   // + keys * (128 B K/V + 4 B mask)
+// fixed part: barriers/alignment + Q buffers (1 or 2 per warpgroup) + 2x2 P buffers;  + keys * (128 B K/V + 4 B mask)
+__host__ __device__ constexpr int v2_fixed_smem(int q_dbuf) { return 1024 + 2 * (1 + q_dbuf) * SQ_BYTES + 2 * 2 * SP2_BYTES; }
 
-__device__ __forceinline__ void wg_barrier(int wg) {
-  asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  if (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// The whole CTA is one continuous stream of 64-key chunks per warpgroup: chunk g = (pass P, chunk c)
+// where a "pass" is one (query tile, query view) pair.  The issuer runs two chunks ahead across pass
+// boundaries (the next pass' Q tile is prefetched into a second buffer while the current one is
+// being processed), so the softmax threads never see a pipeline refill.
+template <bool BF16>
 __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AArgs a) {
   // roles: warps 0-3 = softmax group 0, warps 4-7 = softmax group 1, warp 8 / 9 lane 0 = their MMA issuers
+  // (warps 10, 11 only exist so that the issuers form a full warpgroup for setmaxnreg)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_ch = (a.Lk + CH - 1) / CH;
   const int keys_pad = n_ch * CH;
+  const int q_dbuf = a.q_dbuf;                     // 1: two Q buffers per warpgroup (prefetch distance 1)
   uint8_t* sQ_all = smem;
-  uint8_t* sP_all = sQ_all + 2 * SQ_BYTES;
+  uint8_t* sP_all = sQ_all + 2 * (1 + q_dbuf) * SQ_BYTES;
   uint8_t* sK = sP_all + 4 * SP2_BYTES;
   uint8_t* sV = sK + keys_pad * 64;
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
-  __shared__ uint64_t bar_s[2][2], bar_o[2][2], bar_p[2][2], bar_q[2];
+  __shared__ uint64_t bar_s[2][2], bar_o[2][2], bar_p[2][2], bar_q[2][2];
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
@@ -367,14 +382,14 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   const int head = item % p.heads; item /= p.heads;
   const int win = item % a.n_win;
   const int b = item / a.n_win;
-  const int bf16 = p.dtype;
 
   if (tid == 0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) { mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); mbar_init(&bar_p[i][j], 128); }
-    mbar_init(&bar_q[0], 128); mbar_init(&bar_q[1], 128);
+      for (int j = 0; j < 2; ++j) {
+        mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); mbar_init(&bar_p[i][j], 128); mbar_init(&bar_q[i][j], 128);
+      }
     mbar_fence_init();
   }
   if (warp == 0) {
@@ -385,7 +400,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
   const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
 
-  // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all 256 threads ----------
+  // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all threads -----------------
   for (int idx = tid; idx < keys_pad * 4; idx += V2_THREADS) {
     const int tok = idx >> 2, piece = idx & 3;
     const uint8_t* srcK = kb_;
@@ -421,13 +436,17 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s + wg * 256;   // S0 [0,64) S1 [64,128) O0 [128,160) O1 [160,192)
-  uint8_t* sQ = sQ_all + wg * SQ_BYTES;
+  uint8_t* sQ = sQ_all + wg * (1 + q_dbuf) * SQ_BYTES;
   uint8_t* sP = sP_all + wg * 2 * SP2_BYTES;
   const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
+  const int n_my_tiles = (a.q_tiles - wg + 1) >> 1;      // tiles wg, wg+2, ...
+  const int NP = n_my_tiles * a.q_passes;                // passes of this warpgroup
+  const int total = NP * n_ch;                           // chunks of this warpgroup
 
   if (is_mma) {
     // =============================== MMA issuer of warpgroup `wg` ===========================
-    if ((tid & 31) == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_ISSUER));
+    if (warp < 10 && (tid & 31) == 0 && total > 0) {
       const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
       const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);
@@ -445,224 +464,299 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
             ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
       };
-      auto issue_qk = [&](int c) {       // S(c) = Q K(c)^T  -> S buffer c&1
-        const uint32_t kb = k_addr + c * (CH * 64 / 16);
+      int gq = 0, Pq = 0, cq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
+      auto next_qk = [&]() {                // S(gq) = Q(Pq) K(cq)^T  -> S buffer gq&1
+        if (cq == 0) {
+          mbar_wait(&bar_q[wg][Pq & q_dbuf], (uint32_t)(Pq >> q_dbuf) & 1u);
+          tc_fence_after_sync();
+        }
+        const uint32_t qa = q_addr + (Pq & q_dbuf) * (SQ_BYTES / 16);
+        const uint32_t kb = k_addr + cq * (CH * 64 / 16);
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
-          mma(tmem_base + (c & 1) * CH, qk_lo | (q_addr + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
-        umma_commit(&bar_s[wg][c & 1]);
+          mma(tmem_base + (gq & 1) * CH, qk_lo | (qa + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
+        umma_commit(&bar_s[wg][gq & 1]);
+        ++gq;
+        if (++cq == n_ch) { cq = 0; ++Pq; }
       };
-      auto issue_pv = [&](int c) {       // O(c) = P(c) V(c)  -> O buffer c&1
-        const uint32_t pa = p_addr + (c & 1) * (SP2_BYTES / 16), va = v_addr + c * (CH * 64 / 16);
+      next_qk();
+      if (total > 1) next_qk();
+      int c = 0;
+      for (int g = 0; g < total; ++g) {
+        mbar_wait(&bar_p[wg][g & 1], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) consumed, O(g-2) folded
+        tc_fence_after_sync();
+        {                                                           // O(g) = P(g) V(c)  -> O buffer g&1
+          const uint32_t pa = p_addr + (g & 1) * (SP2_BYTES / 16), va = v_addr + c * (CH * 64 / 16);
 #pragma unroll
-        for (int ks = 0; ks < CH / 16; ++ks)
-          mma(tmem_base + 2 * CH + (c & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
-        umma_commit(&bar_o[wg][c & 1]);
-      };
-      uint32_t ph_q = 0, ph_p[2] = {0, 0};
-      for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
-        for (int pass = 0; pass < a.q_passes; ++pass) {
-          mbar_wait(&bar_q[wg], ph_q);
-          ph_q ^= 1;
-          tc_fence_after_sync();
-          issue_qk(0);
-          if (n_ch > 1) issue_qk(1);
-          for (int c = 0; c < n_ch; ++c) {
-            mbar_wait(&bar_p[wg][c & 1], ph_p[c & 1]);     // P(c) written, S(c) consumed, O(c-2) folded
-            ph_p[c & 1] ^= 1;
-            tc_fence_after_sync();
-            issue_pv(c);
-            if (c + 2 < n_ch) issue_qk(c + 2);
-          }
+          for (int ks = 0; ks < CH / 16; ++ks)
+            mma(tmem_base + 2 * CH + (g & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
+          umma_commit(&bar_o[wg][g & 1]);
         }
+        if (gq < total) next_qk();
+        if (++c == n_ch) c = 0;
       }
     }
   } else {
-  // =============================== softmax warpgroup `wg` ==================================
-  const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-  uint32_t ph_s[2] = {0, 0}, ph_o[2] = {0, 0};
-  const float sl2 = p.scale * 1.4426950408889634f;
-  const bool any_mask = p.key_mask != nullptr;
-  const bool bias_vec = (a.Lk & 3) == 0;
-  bool first_q = true;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_REGS_SOFTMAX));
+    if (total > 0) {
+    // =============================== softmax warpgroup `wg` ==================================
+    // Register-level software pipeline: while the exps of chunk g run on the MUFU, the TMEM loads of
+    // S(g+1) (into the other 64-register array) and of the finished O(g-1) are already in flight, so
+    // no TMEM / mbarrier latency sits between two exp phases.  The loop is unrolled by two so that the
+    // two logit arrays swap roles without register moves.  The per-tile output accumulator (mean over
+    // query views) lives in 32 spare TMEM columns.
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_acc = t_row + 192;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const float L2E = 1.4426950408889634f;
+    const bool any_mask = p.key_mask != nullptr;
+    const bool bias_vec = (a.Lk & 3) == 0;
+    const uint32_t p_row = smem_u32(sP) + (uint32_t)wtid * 128u, p_xor = ((uint32_t)wtid & 7u) << 4;
+    const uint32_t km_s = smem_u32(kmask);
+    const float inv_passes = 1.0f / (float)a.q_passes;
 
-  for (int q_tile = wg; q_tile < a.q_tiles; q_tile += 2) {
-    const int qrow = q_tile * TILE_Q + wtid;
-    const bool row_ok = qrow < rows_per_pass;
-    float acc[DH];
+    // ---- Q tiles: this thread copies 4 x 16 B per pass; the row addresses are computed once per
+    //      query tile (in 16-byte units), a pass (= query view) only adds the plane stride ----------
+    uint32_t qoff16[4];
+    const uint32_t plane16 = p.q_mean ? (uint32_t)(((int64_t)p.qmap.Hv * p.qmap.Wv * p.q_stride) >> 3) : 0u;
+    const uint32_t q_dst = smem_u32(sQ);
+    const int q_issue_c = q_dbuf ? 0 : n_ch - 1;
+    int nq = 0, nq_pass = 0, nq_tile = wg;             // next pass whose Q has not been requested yet
+    auto issue_next_q = [&]() {
+      if (nq_pass == 0) {
 #pragma unroll
-    for (int d = 0; d < DH; ++d) acc[d] = 0.f;
-
-    for (int pass = 0; pass < a.q_passes; ++pass) {
-      // ---- Q tile: 4 lanes per row.  Every MMA that read the previous Q / P / S / O has retired:
-      //      this thread waited on the last s_ready and o_ready of the previous pass. -------------
-      (void)first_q;
+        for (int i = 0; i < 4; ++i) {
+          const int idx = wtid + 128 * i;
+          const int r = idx >> 2, piece = idx & 3;
+          const int rr = nq_tile * TILE_Q + r;
+          qoff16[i] = 0xFFFFFFFFu;
+          if (rr < rows_per_pass) {
+            const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, rr);
+            const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
+            qoff16[i] = (uint32_t)(off >> 3) + piece;
+          }
+        }
+      }
+      const uint32_t dq = q_dst + (uint32_t)(nq & q_dbuf) * SQ_BYTES;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = wtid + 128 * i;
-        const int r = idx >> 2, piece = idx & 3;
-        const int rr = q_tile * TILE_Q + r;
-        const uint8_t* src = qb;
-        uint32_t nb = 0;
-        if (rr < rows_per_pass) {
-          const int t_idx = p.q_mean ? pass * rows_per_pass + rr : rr;
-          const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, t_idx);
-          const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
-          src = qb + off * 2 + piece * 16;
-          nb = 16;
-        }
-        cp_async16(sQ + sw64_off(r, piece), src, nb);
+        const bool ok = qoff16[i] != 0xFFFFFFFFu;
+        const uint8_t* src = ok ? qb + ((size_t)(qoff16[i] + (uint32_t)nq_pass * plane16) << 4) : qb;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + sw64_off(idx >> 2, idx & 3)), "l"(src), "r"(ok ? 16u : 0u) : "memory");
       }
       cp_async_commit();
+      ++nq;
+      if (++nq_pass == a.q_passes) { nq_pass = 0; nq_tile += 2; }
+    };
+    auto complete_q = [&](int Pn) {
       cp_async_wait<0>();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bar_q[wg]);
+      mbar_arrive(&bar_q[wg][Pn & q_dbuf]);
+    };
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
 
-      float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-      float o[DH];
+    int g = 0, c = 0, P = 0, pass = 0, q_tile = wg;      // flat chunk, chunk in pass, flat pass, view, query tile
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, l_fin = 0.f;
+
+    // the pass that just ended ((pass, q_tile) already advanced): out/acc (+)= o / (l * passes)
+    auto finish_pass = [&]() {
+      const float inv = (l_fin > 0.f) ? inv_passes / l_fin : 0.f;
+      const bool last_of_tile = pass == 0;
+      const bool first_of_tile = (last_of_tile ? a.q_passes - 1 : pass - 1) == 0;
+      if (!first_of_tile) {
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_acc, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DH; d += 2)
+          ffma2(o[d], o[d + 1], o[d], o[d + 1], inv, inv, __uint_as_float(ra[d]), __uint_as_float(ra[d + 1]));
+      } else {
+#pragma unroll
+        for (int d = 0; d < DH; d += 2) fmul2(o[d], o[d + 1], o[d], o[d + 1], inv, inv);
+      }
+      if (last_of_tile) {
+        const int qrow = (q_tile - 2) * TILE_Q + wtid;
+        if (qrow < rows_per_pass) {
+          const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
+          int64_t off;
+          if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+          else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+          uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 u;
+            u.x = pack2<BF16>(o[ch * 8 + 0], o[ch * 8 + 1]);
+            u.y = pack2<BF16>(o[ch * 8 + 2], o[ch * 8 + 3]);
+            u.z = pack2<BF16>(o[ch * 8 + 4], o[ch * 8 + 5]);
+            u.w = pack2<BF16>(o[ch * 8 + 6], o[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(op + ch * 16) = u;
+          }
+        }
+      } else {
+        uint32_t ra[32];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) ra[d] = __float_as_uint(o[d]);
+        tmem_st_32x32b_x32(t_acc, ra);
+        tmem_st_wait();
+      }
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    };
 
-      for (int c = 0; c < n_ch; ++c) {
-        const int sb = c & 1;
-        const int key0 = c * CH;
-        const bool use_km = any_mask || (key0 + CH > a.Lk);
-        mbar_wait(&bar_s[wg][sb], ph_s[sb]);
-        ph_s[sb] ^= 1;
-        tc_fence_after_sync();
-        // ---- logits of this row: 64 registers ------------------------------------------
-        float x[CH];
-        {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32b_x32(t_row + sb * CH, r0);
-          tmem_ld_32x32b_x32(t_row + sb * CH + 32, r1);
-          tmem_ld_wait();
+    // one chunk: x = raw logits of chunk g (already in registers), xn <- raw logits of chunk g+1
+    auto step = [&](float (&x)[CH], float (&xn)[CH]) {
+      if (c == 0) { m_run = -INFINITY; l_run = 0.f; }
+      // request the next pass' Q tile: into the other buffer at the first chunk of this pass, or (single
+      // buffer) at the last chunk, when every S = Q K^T of this pass has already been consumed
+      const bool q_now = (c == q_issue_c) && (P + 1 < NP);
+      if (q_now) issue_next_q();
+      const int sb = g & 1;
+      const int key0 = c * CH;
+      const bool use_km = any_mask || (key0 + CH > a.Lk);
+      const bool plain = !use_km && !(p.bias != nullptr);
+      float mx;
+      if (plain) {
+        float mr[4] = {x[0], x[1], x[2], x[3]};          // 4 independent chains (ILP)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(r0[j]); x[32 + j] = __uint_as_float(r1[j]); }
-        }
-        float mx;
-        const bool plain = !use_km && !(p.bias != nullptr);
-        if (plain) {
-          float mr[4] = {x[0], x[1], x[2], x[3]};          // 4 independent chains (ILP)
+        for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+        mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2);
+      } else {
+        if (use_km) {
 #pragma unroll
-          for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
-          mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2);
+          for (int j = 0; j < CH / 4; ++j) {
+            const float4 k4 = lds128f(km_s + (uint32_t)(key0 + 4 * j) * 4u);
+            ffma2(x[4 * j + 0], x[4 * j + 1], x[4 * j + 0], x[4 * j + 1], sl2, sl2, k4.x, k4.y);
+            ffma2(x[4 * j + 2], x[4 * j + 3], x[4 * j + 2], x[4 * j + 3], sl2, sl2, k4.z, k4.w);
+          }
         } else {
-          if (use_km) {
-            const float4* km4 = reinterpret_cast<const float4*>(kmask + key0);
+#pragma unroll
+          for (int j = 0; j < CH; j += 2) fmul2(x[j], x[j + 1], x[j], x[j + 1], sl2, sl2);
+        }
+        const int qrow = q_tile * TILE_Q + wtid;
+        if (p.bias && qrow < rows_per_pass) {
+          const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
+          if (bias_vec && key0 + CH <= a.Lk) {
 #pragma unroll
             for (int j = 0; j < CH / 4; ++j) {
-              const float4 k4 = km4[j];
-              x[4 * j + 0] = fmaf(x[4 * j + 0], sl2, k4.x);
-              x[4 * j + 1] = fmaf(x[4 * j + 1], sl2, k4.y);
-              x[4 * j + 2] = fmaf(x[4 * j + 2], sl2, k4.z);
-              x[4 * j + 3] = fmaf(x[4 * j + 3], sl2, k4.w);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+              ffma2(x[4 * j + 0], x[4 * j + 1], b4.x, b4.y, L2E, L2E, x[4 * j + 0], x[4 * j + 1]);
+              ffma2(x[4 * j + 2], x[4 * j + 3], b4.z, b4.w, L2E, L2E, x[4 * j + 2], x[4 * j + 3]);
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < CH; ++j) x[j] *= sl2;
-          }
-          if (p.bias && row_ok) {
-            const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
-            if (bias_vec && key0 + CH <= a.Lk) {
-#pragma unroll
-              for (int j = 0; j < CH / 4; ++j) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
-                x[4 * j + 0] = fmaf(b4.x, 1.4426950408889634f, x[4 * j + 0]);
-                x[4 * j + 1] = fmaf(b4.y, 1.4426950408889634f, x[4 * j + 1]);
-                x[4 * j + 2] = fmaf(b4.z, 1.4426950408889634f, x[4 * j + 2]);
-                x[4 * j + 3] = fmaf(b4.w, 1.4426950408889634f, x[4 * j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < CH; ++j)
-                if (key0 + j < a.Lk) x[j] = fmaf(__ldg(bp + j), 1.4426950408889634f, x[j]);
-            }
-          }
-          float mr[4] = {x[0], x[1], x[2], x[3]};
-#pragma unroll
-          for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
-          mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
-        }
-        const float m_safe = (mx == -INFINITY) ? 0.f : mx;
-        const float alpha = fast_exp2(m_run - m_safe);
-        float sm[4] = {0.f, 0.f, 0.f, 0.f};
-        if (plain) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(fmaf(x[j], sl2, -m_safe)); sm[j & 3] += x[j]; }
-        } else {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) { x[j] = fast_exp2(x[j] - m_safe); sm[j & 3] += x[j]; }
-        }
-        const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
-        l_run = l_run * alpha + sum;
-        m_run = mx;
-        // P(c) -> smem buffer sb (its previous reader, PV(c-2), retired: this thread folded O(c-2))
-        {
-          uint8_t* dst = sP + sb * SP2_BYTES;
-#pragma unroll
-          for (int cc = 0; cc < CH / 8; ++cc) {
-            uint4 u;
-            u.x = pack_h2(x[cc * 8 + 0], x[cc * 8 + 1], bf16);
-            u.y = pack_h2(x[cc * 8 + 2], x[cc * 8 + 3], bf16);
-            u.z = pack_h2(x[cc * 8 + 4], x[cc * 8 + 5], bf16);
-            u.w = pack_h2(x[cc * 8 + 6], x[cc * 8 + 7], bf16);
-            *reinterpret_cast<uint4*>(dst + sw128_off(wtid, cc)) = u;
+            for (int j = 0; j < CH; ++j)
+              if (key0 + j < a.Lk) x[j] = fmaf(__ldg(bp + j), L2E, x[j]);
           }
         }
-        fence_proxy_async_smem();
-        tc_fence_before_sync();
-        mbar_arrive(&bar_p[wg][sb]);
-        // ---- fold the previous chunk's O into the running output -------------------------
-        if (c > 0) {
-          const int ob = (c - 1) & 1;
-          mbar_wait(&bar_o[wg][ob], ph_o[ob]);
-          ph_o[ob] ^= 1;
-          tc_fence_after_sync();
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, r);
-          tmem_ld_wait();
+        float mr[4] = {x[0], x[1], x[2], x[3]};
 #pragma unroll
-          for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(r[d]));
-          tc_fence_before_sync();
-        }
-        alpha_prev = alpha;
+        for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+        mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
       }
-      {   // last chunk
-        const int ob = (n_ch - 1) & 1;
-        mbar_wait(&bar_o[wg][ob], ph_o[ob]);
-        ph_o[ob] ^= 1;
+      const float m_safe = (mx == -INFINITY) ? 0.f : mx;
+      const float alpha = fast_exp2(m_run - m_safe);
+      const float nm = -m_safe;
+      const float es = plain ? sl2 : 1.0f;              // exp2(x * es - m)
+      float sm[4] = {0.f, 0.f, 0.f, 0.f};
+      auto exps = [&](int j0) {
+#pragma unroll
+        for (int j = j0; j < j0 + CH / 2; j += 4) {
+          ffma2(x[j], x[j + 1], x[j], x[j + 1], es, es, nm, nm);
+          ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
+          x[j] = fast_exp2(x[j]); x[j + 1] = fast_exp2(x[j + 1]);
+          x[j + 2] = fast_exp2(x[j + 2]); x[j + 3] = fast_exp2(x[j + 3]);
+          fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
+          fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
+        }
+      };
+      exps(0);
+      if (q_now) complete_q(P + 1);
+      // ---- prefetch: S(g+1) -> xn (lands under the second half of the exps) ----------------------
+      {
+        // (the loads are unconditional so that xn is defined by them alone -- a predicated load would
+        //  keep both the old and the new 64 registers alive; past the last chunk they read stale columns)
+        const int nb = (g + 1) & 1;
+        if (g + 1 < total) mbar_wait(&bar_s[wg][nb], (uint32_t)((g + 1) >> 1) & 1u);
         tc_fence_after_sync();
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, r);
-        tmem_ld_wait();
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_row + nb * CH, r0);
+        tmem_ld_32x32b_x32(t_row + nb * CH + 32, r1);
 #pragma unroll
-        for (int d = 0; d < DH; ++d) o[d] = fmaf(o[d], alpha_prev, __uint_as_float(r[d]));
-        tc_fence_before_sync();
+        for (int j = 0; j < 32; ++j) { xn[j] = __uint_as_float(r0[j]); xn[32 + j] = __uint_as_float(r1[j]); }
       }
-      const float inv = (l_run > 0.f) ? 1.0f / (l_run * (float)a.q_passes) : 0.f;
+      exps(CH / 2);
+      const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
+      l_run = l_run * alpha + sum;
+      m_run = mx;
+      // P(g) -> smem buffer sb (its previous reader, PV(g-2), retired: this thread folded O(g-2))
+      {
+        const uint32_t dst = p_row + (uint32_t)sb * SP2_BYTES;
 #pragma unroll
-      for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
-    }
+        for (int cc = 0; cc < CH / 8; ++cc)
+          sts128(dst + (((uint32_t)cc << 4) ^ p_xor),
+                 pack2<BF16>(x[cc * 8 + 0], x[cc * 8 + 1]), pack2<BF16>(x[cc * 8 + 2], x[cc * 8 + 3]),
+                 pack2<BF16>(x[cc * 8 + 4], x[cc * 8 + 5]), pack2<BF16>(x[cc * 8 + 6], x[cc * 8 + 7]));
+      }
+      uint32_t ro[32];                      // O(g-1): its load overlaps the proxy fence + arrive
+      {
+        const int ob = (g + 1) & 1;         // == (g - 1) & 1
+        if (g > 0) mbar_wait(&bar_o[wg][ob], (uint32_t)((g - 1) >> 1) & 1u);
+        tc_fence_after_sync();
+        tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, ro);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive(&bar_p[wg][sb]);
+      tmem_ld_wait();                       // xn and ro have landed
+      // ---- fold the previous chunk's O (possibly the previous pass' last) -------------------
+      if (g > 0) {
+#pragma unroll
+        for (int d = 0; d < DH; d += 2)
+          ffma2(o[d], o[d + 1], o[d], o[d + 1], alpha_prev, alpha_prev, __uint_as_float(ro[d]), __uint_as_float(ro[d + 1]));
+        if (c == 0) finish_pass();          // that was the last chunk of the previous pass
+      }
+      alpha_prev = alpha;
+      ++g;
+      if (++c == n_ch) {
+        c = 0; l_fin = l_run; ++P;
+        if (++pass == a.q_passes) { pass = 0; q_tile += 2; }
+      }
+    };
 
-    if (row_ok) {
-      const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
-      int64_t off;
-      if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
-      else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
-      uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+    issue_next_q();
+    complete_q(0);
+    float xa[CH], xb[CH];
+    {
+      mbar_wait(&bar_s[wg][0], 0);
+      tc_fence_after_sync();
+      uint32_t r0[32], r1[32];
+      tmem_ld_32x32b_x32(t_row, r0);
+      tmem_ld_32x32b_x32(t_row + 32, r1);
+      tmem_ld_wait();
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        uint4 u;
-        u.x = pack_h2(acc[ch * 8 + 0], acc[ch * 8 + 1], bf16);
-        u.y = pack_h2(acc[ch * 8 + 2], acc[ch * 8 + 3], bf16);
-        u.z = pack_h2(acc[ch * 8 + 4], acc[ch * 8 + 5], bf16);
-        u.w = pack_h2(acc[ch * 8 + 6], acc[ch * 8 + 7], bf16);
-        *reinterpret_cast<uint4*>(op + ch * 16) = u;
-      }
+      for (int j = 0; j < 32; ++j) { xa[j] = __uint_as_float(r0[j]); xa[32 + j] = __uint_as_float(r1[j]); }
     }
-  }
+    while (g < total) {
+      step(xa, xb);
+      if (g < total) step(xb, xa);
+    }
+    {   // the last chunk's O
+      const int ob = (g - 1) & 1;
+      mbar_wait(&bar_o[wg][ob], (uint32_t)((g - 1) >> 1) & 1u);
+      tc_fence_after_sync();
+      uint32_t ro[32];
+      tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, ro);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < DH; d += 2)
+        ffma2(o[d], o[d + 1], o[d], o[d + 1], alpha_prev, alpha_prev, __uint_as_float(ro[d]), __uint_as_float(ro[d + 1]));
+      finish_pass();
+    }
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -682,6 +776,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   if ((p->k_pad == nullptr) != (p->v_pad == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: k_pad/v_pad must come together");
   AArgs a;
   a.p = *p;
+  a.q_dbuf = 0;
   a.q_nx = qm.H / qm.w1; a.q_ny = qm.W / qm.w2;
   a.k_nx = km.H / km.w1; a.k_ny = km.W / km.w2;
   a.n_win = a.q_nx * a.q_ny;
@@ -708,16 +803,18 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   if (items <= 0 || items > 0x7fffffff) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bad grid");
   if (a.Lk <= KV_CAP_KEYS) {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
-    const int smem = V2_FIXED_SMEM + keys_pad * (128 + 4);
-    static int attr_v2 = 0;
-    if (smem > attr_v2) {
-      cudaError_t e = cudaFuncSetAttribute(window_attn_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    a.q_dbuf = (v2_fixed_smem(1) + keys_pad * (128 + 4) <= 227 * 1024) ? 1 : 0;
+    const int smem = v2_fixed_smem(a.q_dbuf) + keys_pad * (128 + 4);
+    static int attr_v2[2] = {0, 0};
+    auto kern = bf ? window_attn_v2_kernel<true> : window_attn_v2_kernel<false>;
+    if (smem > attr_v2[bf]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
       if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
-      attr_v2 = smem;
+      attr_v2[bf] = smem;
     }
     a.idesc_qk = make_idesc_f16(128, CH, bf, false, false);
     const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
-    window_attn_v2_kernel<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    kern<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     return cobevt::check_launch("window_attn_v2_kernel");
   }
   static bool attr_set = false;

@@ -140,6 +140,8 @@ def ref_attention(q, k, v, qwin, kwin, qgrid, kgrid, heads, scale, q_mean, bias=
     (1, 6, 6, 32, 32, (16, 16), 14, 30, (7, 15), False, True, torch.float16),
     (1, 1, 6, 32, 32, (16, 16), 14, 30, (7, 15), True, True, torch.float16),
     (1, 1, 3, 32, 32, (32, 32), 16, 16, (16, 16), True, True, torch.bfloat16),
+    # exactly 1024 resident keys: single Q buffer variant (no room for the prefetch buffer)
+    (1, 2, 4, 32, 32, (16, 16), 32, 32, (16, 16), False, True, torch.float16),
     # > 1024 keys per window: the streaming (non-resident) kernel
     (1, 2, 3, 24, 24, (24, 24), 20, 20, (20, 20), False, True, torch.float16),
     (1, 1, 5, 16, 16, (16, 16), 15, 15, (15, 15), True, False, torch.float16),
