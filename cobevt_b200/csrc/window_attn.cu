@@ -15,6 +15,8 @@
 // Reference: CrossWinAttention.forward fax_modules.py:198-248, partitions
 // fax_modules.py:399-433; Attention.forward fax_modules.py:132-176;
 // swap_fusion_modules.Attention.forward :87-128.
+#include <cstdlib>
+#include <type_traits>
 #include "sm100.cuh"
 #include "common.h"
 
@@ -34,6 +36,7 @@ constexpr int TMEM_COLS = 256;  // S: [0,128)  O: [128,160)
 struct AArgs {
   CobevtAttnParams p;
   int32_t n_win, q_tiles, Lq, Lk, n_chunks, q_passes, C, q_dbuf;
+  int32_t dbg;   // COBEVT_ATTN_DEBUG (timing experiments only; results are wrong): 1 no MUFU, 2 no P stores, 4 no proxy fence, 8 second warpgroup idle
   int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
   uint32_t idesc_qk, idesc_pv;
 };
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   uint8_t* sK = sP_all + 4 * SP2_BYTES;
   uint8_t* sV = sK + keys_pad * 64;
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
-  __shared__ uint64_t bar_s[2][2], bar_o[2][2], bar_p[2][2], bar_q[2][2];
+  __shared__ __align__(8) uint64_t bars[2][10];    // per warpgroup: S0 S1 | O0 O1 | P0 P1 | Q0 Q1 | F0 F1
+  enum : uint32_t { BAR_S = 0, BAR_O = 16, BAR_P = 32, BAR_Q = 48, BAR_F = 64 };   // byte offsets inside bars[wg]
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
@@ -388,7 +392,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     for (int i = 0; i < 2; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        mbar_init(&bar_s[i][j], 1); mbar_init(&bar_o[i][j], 1); mbar_init(&bar_p[i][j], 128); mbar_init(&bar_q[i][j], 128);
+        mbar_init(&bars[i][j], 1); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
+        mbar_init(&bars[i][8 + j], 128);
       }
     mbar_fence_init();
   }
@@ -439,12 +444,15 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   uint8_t* sQ = sQ_all + wg * (1 + q_dbuf) * SQ_BYTES;
   uint8_t* sP = sP_all + wg * 2 * SP2_BYTES;
   const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
-  const int n_my_tiles = (a.q_tiles - wg + 1) >> 1;      // tiles wg, wg+2, ...
+  const int n_my_tiles = ((a.dbg & 8) && wg == 1) ? 0 : (a.q_tiles - wg + 1) >> 1;      // tiles wg, wg+2, ...
   const int NP = n_my_tiles * a.q_passes;                // passes of this warpgroup
   const int total = NP * n_ch;                           // chunks of this warpgroup
 
   if (is_mma) {
     // =============================== MMA issuer of warpgroup `wg` ===========================
+    // S(k) = Q K(k)^T may overwrite TMEM buffer k&1 as soon as S(k-2) sits in the softmax threads'
+    // registers (barrier F(k-2)); O(g) = P(g) V(g) follows the P(g) barrier.  The softmax threads hold
+    // two chunks of logits in registers, so the issuer runs three chunks ahead of the exps.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_ISSUER));
     if (warp < 10 && (tid & 31) == 0 && total > 0) {
       const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
@@ -466,8 +474,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       };
       int gq = 0, Pq = 0, cq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
       auto next_qk = [&]() {                // S(gq) = Q(Pq) K(cq)^T  -> S buffer gq&1
+        if (gq >= 2) {                      // S(gq-2) has left that buffer
+          mbar_wait(&bars[wg][8 + (gq & 1)], (uint32_t)((gq - 2) >> 1) & 1u);
+          tc_fence_after_sync();
+        }
         if (cq == 0) {
-          mbar_wait(&bar_q[wg][Pq & q_dbuf], (uint32_t)(Pq >> q_dbuf) & 1u);
+          mbar_wait(&bars[wg][6 + (Pq & q_dbuf)], (uint32_t)(Pq >> q_dbuf) & 1u);
           tc_fence_after_sync();
         }
         const uint32_t qa = q_addr + (Pq & q_dbuf) * (SQ_BYTES / 16);
@@ -475,22 +487,23 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
 #pragma unroll
         for (int ks = 0; ks < DH / 16; ++ks)
           mma(tmem_base + (gq & 1) * CH, qk_lo | (qa + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
-        umma_commit(&bar_s[wg][gq & 1]);
+        umma_commit(&bars[wg][gq & 1]);
         ++gq;
         if (++cq == n_ch) { cq = 0; ++Pq; }
       };
       next_qk();
       if (total > 1) next_qk();
+      if (total > 2) next_qk();
       int c = 0;
       for (int g = 0; g < total; ++g) {
-        mbar_wait(&bar_p[wg][g & 1], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) consumed, O(g-2) folded
+        mbar_wait(&bars[wg][4 + (g & 1)], (uint32_t)(g >> 1) & 1u);     // P(g) written, O(g-2) in registers
         tc_fence_after_sync();
         {                                                           // O(g) = P(g) V(c)  -> O buffer g&1
           const uint32_t pa = p_addr + (g & 1) * (SP2_BYTES / 16), va = v_addr + c * (CH * 64 / 16);
 #pragma unroll
           for (int ks = 0; ks < CH / 16; ++ks)
             mma(tmem_base + 2 * CH + (g & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
-          umma_commit(&bar_o[wg][g & 1]);
+          umma_commit(&bars[wg][2 + (g & 1)]);
         }
         if (gq < total) next_qk();
         if (++c == n_ch) c = 0;
@@ -500,18 +513,22 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V2_REGS_SOFTMAX));
     if (total > 0) {
     // =============================== softmax warpgroup `wg` ==================================
-    // Register-level software pipeline: while the exps of chunk g run on the MUFU, the TMEM loads of
-    // S(g+1) (into the other 64-register array) and of the finished O(g-1) are already in flight, so
-    // no TMEM / mbarrier latency sits between two exp phases.  The loop is unrolled by two so that the
-    // two logit arrays swap roles without register moves.  The per-tile output accumulator (mean over
-    // query views) lives in 32 spare TMEM columns.
+    // Register-level software pipeline, one 64-key chunk per step, two chunks of logits in registers:
+    //   x  = S(g)   : exps + P(g) stores (64 MUFU, the step's critical resource)
+    //   xn = S(g+1) : landed under the first exps; its scale / mask / bias / row max run on the ALU
+    //                 pipes in the shadow of the exps of S(g)
+    // and when x is dead it receives S(g+2) straight away.  O(g-1) is read from TMEM under the last
+    // exps.  The only serial pieces of a step are the proxy fence + arrive and the 16-FMA fold of O.
+    // The loop is unrolled by two so the arrays swap roles without register moves; the per-tile output
+    // accumulator (mean over query views) lives in 32 spare TMEM columns.
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     const uint32_t t_acc = t_row + 192;
     const float sl2 = p.scale * 1.4426950408889634f;
     const float L2E = 1.4426950408889634f;
     const bool any_mask = p.key_mask != nullptr;
     const bool bias_vec = (a.Lk & 3) == 0;
-    const uint32_t p_row = smem_u32(sP) + (uint32_t)wtid * 128u, p_xor = ((uint32_t)wtid & 7u) << 4;
+    const uint32_t p_swz = (smem_u32(sP) + (uint32_t)wtid * 128u) | (((uint32_t)wtid & 7u) << 4);
+    const uint32_t bar_wg = smem_u32(&bars[wg][0]);
     const uint32_t km_s = smem_u32(kmask);
     const float inv_passes = 1.0f / (float)a.q_passes;
 
@@ -520,7 +537,10 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     uint32_t qoff16[4];
     const uint32_t plane16 = p.q_mean ? (uint32_t)(((int64_t)p.qmap.Hv * p.qmap.Wv * p.q_stride) >> 3) : 0u;
     const uint32_t q_dst = smem_u32(sQ);
-    const int q_issue_c = q_dbuf ? 0 : n_ch - 1;
+    // S(k) is read from TMEM two steps before its exps, so the Q tile of a pass must be resident two
+    // chunks before the pass starts: request it q_dist passes ahead
+    const int q_dist = (q_dbuf && n_ch == 1) ? 2 : 1;
+    const int q_issue_c = q_dbuf ? 0 : n_ch - 2;       // (single buffer: host guarantees n_ch >= 3)
     int nq = 0, nq_pass = 0, nq_tile = wg;             // next pass whose Q has not been requested yet
     auto issue_next_q = [&]() {
       if (nq_pass == 0) {
@@ -549,18 +569,21 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       ++nq;
       if (++nq_pass == a.q_passes) { nq_pass = 0; nq_tile += 2; }
     };
-    auto complete_q = [&](int Pn) {
+    int nq_done = 0;                                    // passes whose Q has been published to the issuer
+    auto complete_q = [&]() {
       cp_async_wait<0>();
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bar_q[wg][Pn & q_dbuf]);
+      for (; nq_done < nq; ++nq_done) mbar_arrive_a(bar_wg + BAR_Q + (uint32_t)(nq_done & q_dbuf) * 8u);
     };
     float o[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) o[d] = 0.f;
 
     int g = 0, c = 0, P = 0, pass = 0, q_tile = wg;      // flat chunk, chunk in pass, flat pass, view, query tile
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f, l_fin = 0.f;
+    float l_run = 0.f, l_fin = 0.f, alpha_prev = 0.f;
+    float m_cur = -INFINITY, alpha_cur = 0.f;             // running max incl. chunk g / its rescale factor
+    bool plain_cur = true;
 
     // the pass that just ended ((pass, q_tile) already advanced): out/acc (+)= o / (l * passes)
     auto finish_pass = [&]() {
@@ -607,23 +630,19 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       for (int d = 0; d < DH; ++d) o[d] = 0.f;
     };
 
-    // one chunk: x = raw logits of chunk g (already in registers), xn <- raw logits of chunk g+1
-    auto step = [&](float (&x)[CH], float (&xn)[CH]) {
-      if (c == 0) { m_run = -INFINITY; l_run = 0.f; }
-      // request the next pass' Q tile: into the other buffer at the first chunk of this pass, or (single
-      // buffer) at the last chunk, when every S = Q K^T of this pass has already been consumed
-      const bool q_now = (c == q_issue_c) && (P + 1 < NP);
-      if (q_now) issue_next_q();
-      const int sb = g & 1;
-      const int key0 = c * CH;
+    // scale / mask / bias of a chunk of raw logits (chunk `cc` of a pass of query tile `qt`) and its
+    // running row max on top of `m_base`; returns the new running max.  `plain`: x stays raw (the scale
+    // is folded into the exp), otherwise x is rewritten as log2-domain logits.
+    auto prep_max = [&](float (&x)[CH], int cc, int qt, float m_base, bool& plain) -> float {
+      const int key0 = cc * CH;
       const bool use_km = any_mask || (key0 + CH > a.Lk);
-      const bool plain = !use_km && !(p.bias != nullptr);
+      plain = !use_km && !(p.bias != nullptr);
       float mx;
       if (plain) {
         float mr[4] = {x[0], x[1], x[2], x[3]};          // 4 independent chains (ILP)
 #pragma unroll
         for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
-        mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2);
+        mx = fmaxf(m_base, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2);
       } else {
         if (use_km) {
 #pragma unroll
@@ -636,7 +655,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
 #pragma unroll
           for (int j = 0; j < CH; j += 2) fmul2(x[j], x[j + 1], x[j], x[j + 1], sl2, sl2);
         }
-        const int qrow = q_tile * TILE_Q + wtid;
+        const int qrow = qt * TILE_Q + wtid;
         if (p.bias && qrow < rows_per_pass) {
           const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
           if (bias_vec && key0 + CH <= a.Lk) {
@@ -655,63 +674,76 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         float mr[4] = {x[0], x[1], x[2], x[3]};
 #pragma unroll
         for (int j = 4; j < CH; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
-        mx = fmaxf(m_run, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
+        mx = fmaxf(m_base, fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])));
       }
-      const float m_safe = (mx == -INFINITY) ? 0.f : mx;
-      const float alpha = fast_exp2(m_run - m_safe);
+      return mx;
+    };
+
+    // one chunk.  x = logits of chunk g (prepared, max known); xn = raw logits of chunk g+1 (in flight)
+    auto step = [&](auto par_c, float (&x)[CH], float (&xn)[CH]) {
+      constexpr int PAR = decltype(par_c)::value;       // == g & 1: buffer indices are compile-time
+      if (c == 0) l_run = 0.f;
+      const bool q_now = (c == q_issue_c) && (nq < NP) && (nq <= P + q_dist);
+      if (q_now) issue_next_q();            // (the tensor core has finished reading the buffer it overwrites:
+                                            //  this thread has waited for every S of the pass that used it)
+      const float m_safe = (m_cur == -INFINITY) ? 0.f : m_cur;
       const float nm = -m_safe;
-      const float es = plain ? sl2 : 1.0f;              // exp2(x * es - m)
+      const float es = plain_cur ? sl2 : 1.0f;            // exp2(x * es - m)
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
-      auto exps = [&](int j0) {
+      // exps of 8 logits + their 16 bytes of P(g)
+      auto exps8 = [&](int cc) {
+        const int j = cc * 8;
+        ffma2(x[j], x[j + 1], x[j], x[j + 1], es, es, nm, nm);
+        ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
+        ffma2(x[j + 4], x[j + 5], x[j + 4], x[j + 5], es, es, nm, nm);
+        ffma2(x[j + 6], x[j + 7], x[j + 6], x[j + 7], es, es, nm, nm);
+        if (!(a.dbg & 1)) {
 #pragma unroll
-        for (int j = j0; j < j0 + CH / 2; j += 4) {
-          ffma2(x[j], x[j + 1], x[j], x[j + 1], es, es, nm, nm);
-          ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
-          x[j] = fast_exp2(x[j]); x[j + 1] = fast_exp2(x[j + 1]);
-          x[j + 2] = fast_exp2(x[j + 2]); x[j + 3] = fast_exp2(x[j + 3]);
-          fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
-          fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
+          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
         }
+        fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
+        fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
+        fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
+        fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
+        if (!(a.dbg & 2))
+        sts128((p_swz ^ ((uint32_t)cc << 4)) + PAR * SP2_BYTES,
+               pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
+               pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
       };
-      exps(0);
-      if (q_now) complete_q(P + 1);
-      // ---- prefetch: S(g+1) -> xn (lands under the second half of the exps) ----------------------
-      {
-        // (the loads are unconditional so that xn is defined by them alone -- a predicated load would
-        //  keep both the old and the new 64 registers alive; past the last chunk they read stale columns)
-        const int nb = (g + 1) & 1;
-        if (g + 1 < total) mbar_wait(&bar_s[wg][nb], (uint32_t)((g + 1) >> 1) & 1u);
-        tc_fence_after_sync();
-        uint32_t r0[32], r1[32];
-        tmem_ld_32x32b_x32(t_row + nb * CH, r0);
-        tmem_ld_32x32b_x32(t_row + nb * CH + 32, r1);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { xn[j] = __uint_as_float(r0[j]); xn[32 + j] = __uint_as_float(r1[j]); }
+      exps8(0);
+      exps8(1);
+      if (q_now) complete_q();
+      tmem_ld_wait();                        // xn = S(g+1) has landed
+      tc_fence_before_sync();
+      if (g + 1 < total) mbar_arrive_a(bar_wg + BAR_F + (PAR ^ 1) * 8);   // its TMEM buffer is free
+      // ---- exps 16..47, with the preparation of the next chunk in their shadow --------------------
+      exps8(2);
+      exps8(3);
+      float m_next = m_cur, alpha_next = 0.f;
+      bool plain_next = true;
+      if (g + 1 < total) {
+        const bool new_pass = (c + 1 == n_ch);
+        const float m_base = new_pass ? -INFINITY : m_cur;
+        m_next = prep_max(xn, new_pass ? 0 : c + 1, (new_pass && pass + 1 == a.q_passes) ? q_tile + 2 : q_tile, m_base, plain_next);
+        alpha_next = fast_exp2(m_base - ((m_next == -INFINITY) ? 0.f : m_next));
       }
-      exps(CH / 2);
-      const float sum = (sm[0] + sm[1]) + (sm[2] + sm[3]);
-      l_run = l_run * alpha + sum;
-      m_run = mx;
-      // P(g) -> smem buffer sb (its previous reader, PV(g-2), retired: this thread folded O(g-2))
+      exps8(4);
+      exps8(5);
+      // ---- O(g-1): its load lands under the last exps ------------------------------------------
+      uint32_t ro[32];
       {
-        const uint32_t dst = p_row + (uint32_t)sb * SP2_BYTES;
-#pragma unroll
-        for (int cc = 0; cc < CH / 8; ++cc)
-          sts128(dst + (((uint32_t)cc << 4) ^ p_xor),
-                 pack2<BF16>(x[cc * 8 + 0], x[cc * 8 + 1]), pack2<BF16>(x[cc * 8 + 2], x[cc * 8 + 3]),
-                 pack2<BF16>(x[cc * 8 + 4], x[cc * 8 + 5]), pack2<BF16>(x[cc * 8 + 6], x[cc * 8 + 7]));
-      }
-      uint32_t ro[32];                      // O(g-1): its load overlaps the proxy fence + arrive
-      {
-        const int ob = (g + 1) & 1;         // == (g - 1) & 1
-        if (g > 0) mbar_wait(&bar_o[wg][ob], (uint32_t)((g - 1) >> 1) & 1u);
+        constexpr int ob = PAR ^ 1;         // == (g - 1) & 1
+        if (g > 0) mbar_wait_a(bar_wg + BAR_O + ob * 8, (uint32_t)((g - 1) >> 1) & 1u);
         tc_fence_after_sync();
         tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, ro);
       }
-      fence_proxy_async_smem();
+      exps8(6);
+      exps8(7);
+      l_run = l_run * alpha_cur + ((sm[0] + sm[1]) + (sm[2] + sm[3]));
+      if (!(a.dbg & 4)) fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive(&bar_p[wg][sb]);
-      tmem_ld_wait();                       // xn and ro have landed
+      mbar_arrive_a(bar_wg + BAR_P + PAR * 8);
+      tmem_ld_wait();                       // ro has landed
       // ---- fold the previous chunk's O (possibly the previous pass' last) -------------------
       if (g > 0) {
 #pragma unroll
@@ -719,7 +751,18 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
           ffma2(o[d], o[d + 1], o[d], o[d + 1], alpha_prev, alpha_prev, __uint_as_float(ro[d]), __uint_as_float(ro[d + 1]));
         if (c == 0) finish_pass();          // that was the last chunk of the previous pass
       }
-      alpha_prev = alpha;
+      // ---- x is dead: it receives S(g+2) ------------------------------------------------------
+      {
+        if (g + 2 < total) mbar_wait_a(bar_wg + BAR_S + PAR * 8, (uint32_t)((g + 2) >> 1) & 1u);
+        tc_fence_after_sync();
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_row + PAR * CH, r0);
+        tmem_ld_32x32b_x32(t_row + PAR * CH + 32, r1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(r0[j]); x[32 + j] = __uint_as_float(r1[j]); }
+      }
+      alpha_prev = alpha_cur;
+      m_cur = m_next; alpha_cur = alpha_next; plain_cur = plain_next;
       ++g;
       if (++c == n_ch) {
         c = 0; l_fin = l_run; ++P;
@@ -727,11 +770,13 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       }
     };
 
+    // ---- prologue: Q of the first pass(es), S(0) prepared, S(1) in flight -------------------------
     issue_next_q();
-    complete_q(0);
+    if (q_dist == 2 && NP > 1) issue_next_q();
+    complete_q();
     float xa[CH], xb[CH];
     {
-      mbar_wait(&bar_s[wg][0], 0);
+      mbar_wait_a(bar_wg + BAR_S, 0);
       tc_fence_after_sync();
       uint32_t r0[32], r1[32];
       tmem_ld_32x32b_x32(t_row, r0);
@@ -739,14 +784,26 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j) { xa[j] = __uint_as_float(r0[j]); xa[32 + j] = __uint_as_float(r1[j]); }
+      tc_fence_before_sync();
+      mbar_arrive_a(bar_wg + BAR_F);
+      m_cur = prep_max(xa, 0, q_tile, -INFINITY, plain_cur);
+      alpha_cur = 0.f;
+      if (total > 1) mbar_wait_a(bar_wg + BAR_S + 8, 0);
+      tc_fence_after_sync();
+      uint32_t s0[32], s1[32];
+      tmem_ld_32x32b_x32(t_row + CH, s0);
+      tmem_ld_32x32b_x32(t_row + CH + 32, s1);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { xb[j] = __uint_as_float(s0[j]); xb[32 + j] = __uint_as_float(s1[j]); }
     }
     while (g < total) {
-      step(xa, xb);
-      if (g < total) step(xb, xa);
+      step(std::integral_constant<int, 0>{}, xa, xb);
+      if (g < total) step(std::integral_constant<int, 1>{}, xb, xa);
     }
+    tmem_ld_wait();                          // drain the last (stale) logit prefetch
     {   // the last chunk's O
       const int ob = (g - 1) & 1;
-      mbar_wait(&bar_o[wg][ob], (uint32_t)((g - 1) >> 1) & 1u);
+      mbar_wait_a(bar_wg + BAR_O + (uint32_t)ob * 8u, (uint32_t)((g - 1) >> 1) & 1u);
       tc_fence_after_sync();
       uint32_t ro[32];
       tmem_ld_32x32b_x32(t_row + 2 * CH + ob * DH, ro);
@@ -777,6 +834,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   AArgs a;
   a.p = *p;
   a.q_dbuf = 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   a.q_nx = qm.H / qm.w1; a.q_ny = qm.W / qm.w2;
   a.k_nx = km.H / km.w1; a.k_ny = km.W / km.w2;
   a.n_win = a.q_nx * a.q_ny;
