@@ -820,6 +820,500 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
   if (warp == 0) tmem_dealloc(tmem_base_s, 512);
 }
 
+// =====================================================================================
+// Four-warpgroup resident-KV kernel.  The softmax of this head size (32) is bound by per-warp
+// instruction latency, not by any pipe: one query row per thread needs ~100 registers for a 32-key
+// chunk, so four softmax warpgroups (16 warps, 112 registers each) fit where the two-warpgroup
+// kernel above (64-key chunks, 224 registers) has only 8 warps to hide its dependency chains.
+//   warps 0-15   softmax warpgroups 0..3        warps 16-19   lane 0 = MMA issuer of warpgroup (warp-16)
+// Work split inside the CTA (one CTA = one (batch row, window, head), K/V resident as above):
+//   * >= 3 query tiles: warpgroup w takes tiles w, w+4, ... with all their passes (query views);
+//   * 1 or 2 query tiles: the G = 4 / tiles warpgroups that share a tile split its passes (mean over
+//     query views: partial means add up) or, with a single pass, its key chunks (independent online
+//     softmax streams, log-sum-exp merge); the partials meet once, at the end, through shared memory.
+// TMEM per warpgroup (128 columns): S0 [0,32) S1 [32,64) O [64,96) ACC [96,128).  O accumulates in TMEM over
+// the chunks of a pass (lazy rescale, see below): no tensor-core round trip sits on the per-chunk path.
+// =====================================================================================
+constexpr int CH3 = 32;                                  // keys per chunk
+constexpr int V3_WG = 4;
+constexpr int V3_THREADS = (V3_WG + 1) * 128;            // 640
+constexpr int V3_REGS_SOFTMAX = 112, V3_REGS_ISSUER = 32;   // the CTA pool is 640 x 96 = 61440 = 16*32*112 + 4*32*32
+constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 8 KB per P buffer
+__host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + 2 * SP3_BYTES); }
+
+template <bool BF16>
+__global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int n_ch = (a.Lk + CH3 - 1) / CH3;
+  const int keys_pad = n_ch * CH3;
+  uint8_t* sQ_all = smem;                                   // per warpgroup: 2 x 8 KB
+  uint8_t* sP_all = sQ_all + V3_WG * 2 * SQ_BYTES;          // per warpgroup: 2 x 8 KB (also the merge scratch)
+  uint8_t* sK = sP_all + V3_WG * 2 * SP3_BYTES;
+  uint8_t* sV = sK + keys_pad * 64;
+  float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
+  __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S0 S1 | O0 O1 | P0 P1 | Q0 Q1
+  enum : uint32_t { BAR_S = 0, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
+  __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
+  __shared__ uint32_t tmem_base_s;
+
+  const CobevtAttnParams& p = a.p;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool is_mma = warp >= 4 * V3_WG;
+  const int wg = is_mma ? warp - 4 * V3_WG : warp >> 2, wtid = tid & 127;
+  int item = blockIdx.x;
+  const int head = item % p.heads; item /= p.heads;
+  const int win = item % a.n_win;
+  const int b = item / a.n_win;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < V3_WG; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        mbar_init(&bars[i][j], 1); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
+      }
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q);
+  const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
+  const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
+
+  // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all threads -----------------
+  for (int idx = tid; idx < keys_pad * 4; idx += V3_THREADS) {
+    const int tok = idx >> 2, piece = idx & 3;
+    const uint8_t* srcK = kb_;
+    const uint8_t* srcV = vb_;
+    uint32_t nb = 0;
+    float km = 0.f;
+    if (tok < a.Lk) {
+      const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, tok);
+      if (t.in_range) {
+        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kv_stride + head * DH;
+        srcK = kb_ + off * 2 + piece * 16;
+        srcV = vb_ + off * 2 + piece * 16;
+        nb = 16;
+        if (p.key_mask && piece == 0 &&
+            p.key_mask[(((int64_t)b * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kvmap.views + t.n] == 0)
+          km = -INFINITY;
+      } else if (p.k_pad) {
+        srcK = reinterpret_cast<const uint8_t*>(p.k_pad) + head * DH * 2 + piece * 16;
+        srcV = reinterpret_cast<const uint8_t*>(p.v_pad) + head * DH * 2 + piece * 16;
+        nb = 16;
+      }
+    } else {
+      km = -INFINITY;
+    }
+    cp_async16(sK + sw64_off(tok, piece), srcK, nb);
+    cp_async16(sV + sw64_off(tok, piece), srcV, nb);
+    if (piece == 0) kmask[tok] = km;
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s + wg * 128;
+  uint8_t* sQ = sQ_all + wg * 2 * SQ_BYTES;
+  uint8_t* sP = sP_all + wg * 2 * SP3_BYTES;
+  const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
+
+  // ---- work split ---------------------------------------------------------------------------
+  const int T = a.q_tiles >= 3 ? V3_WG : a.q_tiles;       // warpgroups are spread over T tiles at a time
+  const int G = V3_WG / T;                                // warpgroups sharing one tile (1, 2 or 4)
+  const int t0 = wg % T, sub = wg / T;
+  const bool split_pass = G > 1 && a.q_passes > 1;        // the group splits the query views
+  const bool split_keys = G > 1 && a.q_passes == 1;       // the group splits the key chunks
+  const int n_my_tiles = t0 < a.q_tiles ? (a.q_tiles - t0 + T - 1) / T : 0;    // == 1 whenever G > 1
+  const int passes_per_tile = split_pass ? (a.q_passes > sub ? (a.q_passes - sub + G - 1) / G : 0) : a.q_passes;
+  const int n_uch = split_keys ? (n_ch > sub ? (n_ch - sub + G - 1) / G : 0) : n_ch;   // chunks per pass
+  const int c_first = split_keys ? sub : 0, c_step = split_keys ? G : 1;
+  const int NP = n_my_tiles * passes_per_tile;
+  const int total = ((a.dbg & 8) && wg > 0) ? 0 : NP * n_uch;
+
+  if (is_mma) {
+    // =============================== MMA issuer of warpgroup `wg` ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V3_REGS_ISSUER));
+    if ((tid & 31) == 0 && total > 0) {
+      const uint64_t dA = make_smem_desc(0, 16, 512, LAYOUT_SW64);      // Q, K, P: K-major 64-byte rows
+      const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);     // V: MN-major
+      const uint32_t a_lo = (uint32_t)dA, a_hi = (uint32_t)(dA >> 32);
+      const uint32_t v_lo = (uint32_t)dV, v_hi = (uint32_t)(dV >> 32);
+      const uint32_t q_addr = smem_u32(sQ) >> 4, k_addr = smem_u32(sK) >> 4, v_addr = smem_u32(sV) >> 4;
+      const uint32_t p_addr = smem_u32(sP) >> 4;
+      auto mma = [&](uint32_t d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t acc) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+            ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
+      };
+      int gq = 0, Pq = 0, kq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
+      auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T  -> S buffer gq&1
+        if (kq == 0) {
+          mbar_wait(&bars[wg][6 + (Pq & 1)], (uint32_t)(Pq >> 1) & 1u);
+          tc_fence_after_sync();
+        }
+        const uint32_t qa = q_addr + (Pq & 1) * (SQ_BYTES / 16);
+        const uint32_t kb = k_addr + (c_first + kq * c_step) * (CH3 * 64 / 16);
+#pragma unroll
+        for (int ks = 0; ks < DH / 16; ++ks)
+          mma(tmem_base + (gq & 1) * CH3, a_lo | (qa + ks * 2), a_hi, a_lo | (kb + ks * 2), a_hi, a.idesc_qk, ks ? 1u : 0u);
+        umma_commit(&bars[wg][gq & 1]);
+        ++gq;
+        if (++kq == n_uch) { kq = 0; ++Pq; }
+      };
+      next_qk();
+      if (total > 1) next_qk();
+      int k = 0;
+      for (int g = 0; g < total; ++g) {
+        mbar_wait(&bars[wg][4 + (g & 1)], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) and O(g-1) consumed
+        tc_fence_after_sync();
+        {                                                           // O = P(g) V(chunk)
+          const uint32_t pa = p_addr + (g & 1) * (SP3_BYTES / 16), va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
+#pragma unroll
+          for (int ks = 0; ks < CH3 / 16; ++ks)
+            mma(tmem_base + 2 * CH3, a_lo | (pa + ks * 2), a_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, (k | ks) ? 1u : 0u);
+          umma_commit(&bars[wg][2 + (g & 1)]);
+        }
+        if (gq < total) next_qk();
+        if (++k == n_uch) k = 0;
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V3_REGS_SOFTMAX));
+    // =============================== softmax warpgroup `wg` ==================================
+    const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t t_o = t_row + 2 * CH3, t_acc = t_row + 2 * CH3 + DH;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const float L2E = 1.4426950408889634f;
+    const bool any_mask = p.key_mask != nullptr;
+    const bool bias_vec = (a.Lk & 3) == 0;
+    const uint32_t p_swz = (smem_u32(sP) + (uint32_t)wtid * 64u) | ((((uint32_t)wtid >> 1) & 3u) << 4);   // SW64 row
+    const uint32_t bar_wg = smem_u32(&bars[wg][0]);
+    const uint32_t km_s = smem_u32(kmask);
+    const float inv_passes = 1.0f / (float)a.q_passes;
+    float o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    float m_fin = -INFINITY, l_fin = 0.f;                  // state of the last finished pass
+    bool have_acc = false;                                 // ACC (TMEM) holds earlier passes of the current tile
+
+    if (total > 0) {
+    // ---- Q tiles (see the two-warpgroup kernel) -------------------------------------------------
+    uint32_t qoff16[4];
+    const uint32_t plane16 = p.q_mean ? (uint32_t)(((int64_t)p.qmap.Hv * p.qmap.Wv * p.q_stride) >> 3) : 0u;
+    const uint32_t q_dst = smem_u32(sQ);
+    int nq = 0, nq_pj = 0, nq_tile = t0;               // next pass whose Q has not been requested yet
+    auto issue_next_q = [&]() {
+      if (nq_pj == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = wtid + 128 * i;
+          const int r = idx >> 2, piece = idx & 3;
+          const int rr = nq_tile * TILE_Q + r;
+          qoff16[i] = 0xFFFFFFFFu;
+          if (rr < rows_per_pass) {
+            const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, rr);
+            const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
+            qoff16[i] = (uint32_t)(off >> 3) + piece;
+          }
+        }
+      }
+      const uint32_t view = split_pass ? (uint32_t)(sub + nq_pj * G) : (uint32_t)nq_pj;
+      const uint32_t dq = q_dst + (uint32_t)(nq & 1) * SQ_BYTES;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int idx = wtid + 128 * i;
+        const bool ok = qoff16[i] != 0xFFFFFFFFu;
+        const uint8_t* src = ok ? qb + ((size_t)(qoff16[i] + view * plane16) << 4) : qb;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + sw64_off(idx >> 2, idx & 3)), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
+      cp_async_commit();
+      ++nq;
+      if (++nq_pj == passes_per_tile) { nq_pj = 0; nq_tile += T; }
+    };
+    auto complete_q = [&](int Pn) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive_a(bar_wg + BAR_Q + (uint32_t)(Pn & 1) * 8u);
+    };
+    auto write_rows = [&](int q_tile) {                    // o -> output rows of query tile q_tile
+      const int qrow = q_tile * TILE_Q + wtid;
+      if (qrow < rows_per_pass) {
+        const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
+        int64_t off;
+        if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+        else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+        uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 u;
+          u.x = pack2<BF16>(o[ch * 8 + 0], o[ch * 8 + 1]);
+          u.y = pack2<BF16>(o[ch * 8 + 2], o[ch * 8 + 3]);
+          u.z = pack2<BF16>(o[ch * 8 + 4], o[ch * 8 + 5]);
+          u.w = pack2<BF16>(o[ch * 8 + 6], o[ch * 8 + 7]);
+          *reinterpret_cast<uint4*>(op + ch * 16) = u;
+        }
+      }
+    };
+
+    int g = 0, k = 0, P = 0, pj = 0, q_tile = t0;        // flat chunk, chunk in pass, flat pass, pass in tile, tile
+    float m_run = 0.f, l_run = 0.f;
+
+    // the pass that just ended ((pj, q_tile) already advanced).  Key split: keep (m, l, o) raw for the
+    // merge.  Otherwise o <- o / (l * passes) + earlier passes of this tile; the tile's last pass leaves
+    // the sum in `o` (written out, or handed to the pass-split merge), the others park it in TMEM.
+    auto finish_pass = [&](bool last_unit) {
+      if (split_keys) return;
+      const float inv = (l_fin > 0.f) ? inv_passes / l_fin : 0.f;
+      const bool last_of_tile = last_unit || pj == 0;
+      if (have_acc) {
+        uint32_t ra[32];
+        tmem_ld_32x32b_x32(t_acc, ra);
+        tmem_ld_wait();
+#pragma unroll
+        for (int d = 0; d < DH; d += 2)
+          ffma2(o[d], o[d + 1], o[d], o[d + 1], inv, inv, __uint_as_float(ra[d]), __uint_as_float(ra[d + 1]));
+      } else {
+#pragma unroll
+        for (int d = 0; d < DH; d += 2) fmul2(o[d], o[d + 1], o[d], o[d + 1], inv, inv);
+      }
+      if (last_of_tile) {
+        have_acc = false;
+        if (G == 1) {
+          write_rows(last_unit ? q_tile : q_tile - T);
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] = 0.f;
+        }
+      } else {
+        uint32_t ra[32];
+#pragma unroll
+        for (int d = 0; d < DH; ++d) ra[d] = __float_as_uint(o[d]);
+        tmem_st_32x32b_x32(t_acc, ra);
+        tmem_st_wait();
+        have_acc = true;
+#pragma unroll
+        for (int d = 0; d < DH; ++d) o[d] = 0.f;
+      }
+    };
+    // the finished pass' O: TMEM -> o
+    auto load_o = [&](int glast) {
+      mbar_wait_a(bar_wg + BAR_O + (uint32_t)(glast & 1) * 8u, (uint32_t)(glast >> 1) & 1u);
+      tc_fence_after_sync();
+      uint32_t ro[32];
+      tmem_ld_32x32b_x32(t_o, ro);
+      tmem_ld_wait();
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] = __uint_as_float(ro[d]);
+      tc_fence_before_sync();
+    };
+
+    issue_next_q();
+    complete_q(0);
+    for (; g < total; ++g) {
+      const bool q_now = (k == 0) && (P + 1 < NP);
+      if (q_now) issue_next_q();
+      const int sb = g & 1;
+      const int key0 = (c_first + k * c_step) * CH3;
+      mbar_wait_a(bar_wg + BAR_S + (uint32_t)sb * 8u, (uint32_t)(g >> 1) & 1u);
+      tc_fence_after_sync();
+      float x[CH3];
+      {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_row + sb * CH3, r0);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < CH3; ++j) x[j] = __uint_as_float(r0[j]);
+      }
+      const bool use_km = any_mask || (key0 + CH3 > a.Lk);
+      const bool plain = !use_km && !(p.bias != nullptr);
+      float cmax;                                   // chunk max, log2 domain
+      if (plain) {
+        float mr[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+        for (int j = 4; j < CH3; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+        cmax = fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3])) * sl2;
+      } else {
+        if (use_km) {
+#pragma unroll
+          for (int j = 0; j < CH3 / 4; ++j) {
+            const float4 k4 = lds128f(km_s + (uint32_t)(key0 + 4 * j) * 4u);
+            ffma2(x[4 * j + 0], x[4 * j + 1], x[4 * j + 0], x[4 * j + 1], sl2, sl2, k4.x, k4.y);
+            ffma2(x[4 * j + 2], x[4 * j + 3], x[4 * j + 2], x[4 * j + 3], sl2, sl2, k4.z, k4.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CH3; j += 2) fmul2(x[j], x[j + 1], x[j], x[j + 1], sl2, sl2);
+        }
+        const int qrow = q_tile * TILE_Q + wtid;
+        if (p.bias && qrow < rows_per_pass) {
+          const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
+          if (bias_vec && key0 + CH3 <= a.Lk) {
+#pragma unroll
+            for (int j = 0; j < CH3 / 4; ++j) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+              ffma2(x[4 * j + 0], x[4 * j + 1], b4.x, b4.y, L2E, L2E, x[4 * j + 0], x[4 * j + 1]);
+              ffma2(x[4 * j + 2], x[4 * j + 3], b4.z, b4.w, L2E, L2E, x[4 * j + 2], x[4 * j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH3; ++j)
+              if (key0 + j < a.Lk) x[j] = fmaf(__ldg(bp + j), L2E, x[j]);
+          }
+        }
+        float mr[4] = {x[0], x[1], x[2], x[3]};
+#pragma unroll
+        for (int j = 4; j < CH3; ++j) mr[j & 3] = fmaxf(mr[j & 3], x[j]);
+        cmax = fmaxf(fmaxf(mr[0], mr[1]), fmaxf(mr[2], mr[3]));
+      }
+      // ---- reference max.  O accumulates in TMEM across the chunks of a pass, so the exps stay relative
+      //      to a *stale* reference m_run and O is only rescaled when the row max has grown by more than
+      //      2^8 (P <= 256 is harmless in 16 bits; sums and O are fp32).  The result is the exact softmax.
+      if (k == 0) {
+        m_run = (cmax == -INFINITY) ? 0.f : cmax;
+        l_run = 0.f;
+      } else {
+        const bool grow = cmax > m_run + 8.0f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float fac = grow ? fast_exp2(m_run - cmax) : 1.0f;
+          if (grow) m_run = cmax;
+          l_run *= fac;
+          // every P V issued so far (chunks <= g-1) must have landed before O is touched
+          mbar_wait_a(bar_wg + BAR_O + (uint32_t)((g - 1) & 1) * 8u, (uint32_t)((g - 1) >> 1) & 1u);
+          tc_fence_after_sync();
+          uint32_t ro[32];
+          tmem_ld_32x32b_x32(t_o, ro);
+          tmem_ld_wait();
+#pragma unroll
+          for (int d = 0; d < DH; ++d) ro[d] = __float_as_uint(__uint_as_float(ro[d]) * fac);
+          tmem_st_32x32b_x32(t_o, ro);
+          tmem_st_wait();
+          tc_fence_before_sync();
+        }
+      }
+      const float nm = -m_run;
+      const float es = plain ? sl2 : 1.0f;
+      // P buffer sb was last read by P V of chunk g-2
+      if (g >= 2) mbar_wait_a(bar_wg + BAR_O + (uint32_t)sb * 8u, (uint32_t)((g - 2) >> 1) & 1u);
+      float sm[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t p_dst = p_swz + (uint32_t)sb * SP3_BYTES;
+#pragma unroll
+      for (int cc = 0; cc < CH3 / 8; ++cc) {
+        const int j = cc * 8;
+        ffma2(x[j], x[j + 1], x[j], x[j + 1], es, es, nm, nm);
+        ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
+        ffma2(x[j + 4], x[j + 5], x[j + 4], x[j + 5], es, es, nm, nm);
+        ffma2(x[j + 6], x[j + 7], x[j + 6], x[j + 7], es, es, nm, nm);
+        if (!(a.dbg & 1)) {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
+        }
+        fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
+        fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
+        fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
+        fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
+        if (!(a.dbg & 2))
+        sts128(p_dst ^ ((uint32_t)cc << 4),
+               pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
+               pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
+      }
+      l_run += (sm[0] + sm[1]) + (sm[2] + sm[3]);
+      if (q_now) complete_q(P + 1);
+      // ---- a new pass overwrites O: the finished one has to leave TMEM first ----------------------
+      if (k == 0 && g > 0) {
+        load_o(g - 1);
+        finish_pass(false);
+      }
+      if (!(a.dbg & 4)) fence_proxy_async_smem();
+      tc_fence_before_sync();
+      mbar_arrive_a(bar_wg + BAR_P + (uint32_t)sb * 8u);
+      if (++k == n_uch) {
+        k = 0; l_fin = l_run; m_fin = m_run; ++P;
+        if (++pj == passes_per_tile) { pj = 0; q_tile += T; }
+      }
+    }
+    load_o(g - 1);
+    if (pj == 0) q_tile -= T;                  // back to the tile of the last pass
+    finish_pass(true);
+    }
+
+    // ---- partials of a shared tile meet here ---------------------------------------------------
+    if (G > 1) {
+      if (sub > 0) {                            // park (m, l, o) in this warpgroup's P buffers (all its MMAs retired)
+        const uint32_t base = smem_u32(sP) + (uint32_t)wtid * 128u;
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch)
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (((uint32_t)ch ^ ((uint32_t)wtid & 7u)) << 4)),
+                       "f"(o[ch * 4 + 0]), "f"(o[ch * 4 + 1]), "f"(o[ch * 4 + 2]), "f"(o[ch * 4 + 3]) : "memory");
+        sML[wg][wtid] = make_float2(m_fin, l_fin);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + t0), "r"(G * 128) : "memory");
+      if (sub == 0) {
+        float m_all = m_fin, l_all = l_fin;
+        if (split_keys) {
+          for (int s = 1; s < G; ++s) m_all = fmaxf(m_all, sML[t0 + s * T][wtid].x);
+          const float ms = (m_all == -INFINITY) ? 0.f : m_all;
+          const float w0 = fast_exp2(m_fin - ms);
+          l_all = l_fin * w0;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] *= w0;
+        }
+        for (int s = 1; s < G; ++s) {
+          const int ow = t0 + s * T;
+          const float2 ml = sML[ow][wtid];
+          const float ms = (m_all == -INFINITY) ? 0.f : m_all;
+          const float ws = split_keys ? fast_exp2(ml.x - ms) : 1.0f;
+          if (split_keys) l_all = fmaf(ml.y, ws, l_all);
+          const uint32_t base = smem_u32(sP_all + ow * 2 * SP3_BYTES) + (uint32_t)wtid * 128u;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const float4 f = lds128f(base + (((uint32_t)ch ^ ((uint32_t)wtid & 7u)) << 4));
+            o[ch * 4 + 0] = fmaf(f.x, ws, o[ch * 4 + 0]);
+            o[ch * 4 + 1] = fmaf(f.y, ws, o[ch * 4 + 1]);
+            o[ch * 4 + 2] = fmaf(f.z, ws, o[ch * 4 + 2]);
+            o[ch * 4 + 3] = fmaf(f.w, ws, o[ch * 4 + 3]);
+          }
+        }
+        if (split_keys) {
+          const float inv = l_all > 0.f ? 1.0f / l_all : 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) o[d] *= inv;
+        }
+        // rows of tile t0 (token addressing as in write_rows)
+        const int qrow = t0 * TILE_Q + wtid;
+        if (qrow < rows_per_pass) {
+          const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
+          int64_t off;
+          if (p.q_mean) off = (((int64_t)b * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+          else off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.out_stride + head * DH;
+          uint8_t* op = reinterpret_cast<uint8_t*>(p.out) + off * 2;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 u;
+            u.x = pack2<BF16>(o[ch * 8 + 0], o[ch * 8 + 1]);
+            u.y = pack2<BF16>(o[ch * 8 + 2], o[ch * 8 + 3]);
+            u.z = pack2<BF16>(o[ch * 8 + 4], o[ch * 8 + 5]);
+            u.w = pack2<BF16>(o[ch * 8 + 6], o[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(op + ch * 16) = u;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base_s, 512);
+}
+
 }  // namespace
 
 extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
@@ -859,6 +1353,26 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.idesc_pv = make_idesc_f16(128, DH, bf, false, true);
   const int64_t items = (int64_t)p->B * a.n_win * p->heads * a.q_tiles;
   if (items <= 0 || items > 0x7fffffff) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bad grid");
+  static int force_kernel = -1;     // COBEVT_ATTN_KERNEL=2 forces the two-warpgroup kernel (A/B timing)
+  if (force_kernel < 0) { const char* e = getenv("COBEVT_ATTN_KERNEL"); force_kernel = e ? atoi(e) : 0; }
+  {
+    const int keys_pad = cobevt::ceil_div(a.Lk, CH3) * CH3;
+    const int smem = v3_fixed_smem() + keys_pad * (128 + 4);
+    if (smem <= 227 * 1024 && force_kernel != 2) {
+      static int attr_v3[2] = {0, 0};
+      auto kern = bf ? window_attn_v3_kernel<true> : window_attn_v3_kernel<false>;
+      if (smem > attr_v3[bf]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
+        attr_v3[bf] = smem;
+      }
+      a.q_dbuf = 1;
+      a.idesc_qk = make_idesc_f16(128, CH3, bf, false, false);
+      const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
+      kern<<<(unsigned)ctas, V3_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+      return cobevt::check_launch("window_attn_v3_kernel");
+    }
+  }
   if (a.Lk <= KV_CAP_KEYS) {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
     a.q_dbuf = (v2_fixed_smem(1) + keys_pad * (128 + 4) <= 227 * 1024) ? 1 : 0;
