@@ -76,6 +76,20 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
   }
 }
 
+// Unbounded variant for the innermost loops of kernels whose protocol is covered by the bounded waits
+// elsewhere (three instructions per retry; try_wait itself suspends the thread in hardware).
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar_addr), "r"(parity)
+      : "memory");
+}
+
 // ----------------------------------------------------------------------------
 // proxy / tcgen05 fences
 // ----------------------------------------------------------------------------

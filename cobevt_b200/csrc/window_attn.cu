@@ -1000,9 +1000,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
     const uint32_t bar_wg = smem_u32(&bars[wg][0]);
     const uint32_t km_s = smem_u32(kmask);
     const float inv_passes = 1.0f / (float)a.q_passes;
-    float o[DH];
-#pragma unroll
-    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    float o[DH];                                           // the warpgroup's last (or only) tile result
     float m_fin = -INFINITY, l_fin = 0.f;                  // state of the last finished pass
     bool have_acc = false;                                 // ACC (TMEM) holds earlier passes of the current tile
 
@@ -1046,7 +1044,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       tc_fence_before_sync();
       mbar_arrive_a(bar_wg + BAR_Q + (uint32_t)(Pn & 1) * 8u);
     };
-    auto write_rows = [&](int q_tile) {                    // o -> output rows of query tile q_tile
+    auto write_rows = [&](int q_tile, float (&o)[DH]) {    // o -> output rows of query tile q_tile
       const int qrow = q_tile * TILE_Q + wtid;
       if (qrow < rows_per_pass) {
         const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, qrow);
@@ -1072,7 +1070,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
     // the pass that just ended ((pj, q_tile) already advanced).  Key split: keep (m, l, o) raw for the
     // merge.  Otherwise o <- o / (l * passes) + earlier passes of this tile; the tile's last pass leaves
     // the sum in `o` (written out, or handed to the pass-split merge), the others park it in TMEM.
-    auto finish_pass = [&](bool last_unit) {
+    auto finish_pass = [&](bool last_unit, float (&o)[DH]) {
       if (split_keys) return;
       const float inv = (l_fin > 0.f) ? inv_passes / l_fin : 0.f;
       const bool last_of_tile = last_unit || pj == 0;
@@ -1090,9 +1088,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       if (last_of_tile) {
         have_acc = false;
         if (G == 1) {
-          write_rows(last_unit ? q_tile : q_tile - T);
-#pragma unroll
-          for (int d = 0; d < DH; ++d) o[d] = 0.f;
+          write_rows(last_unit ? q_tile : q_tile - T, o);
         }
       } else {
         uint32_t ra[32];
@@ -1101,12 +1097,10 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
         tmem_st_32x32b_x32(t_acc, ra);
         tmem_st_wait();
         have_acc = true;
-#pragma unroll
-        for (int d = 0; d < DH; ++d) o[d] = 0.f;
       }
     };
     // the finished pass' O: TMEM -> o
-    auto load_o = [&](int glast) {
+    auto load_o = [&](int glast, float (&o)[DH]) {
       mbar_wait_a(bar_wg + BAR_O + (uint32_t)(glast & 1) * 8u, (uint32_t)(glast >> 1) & 1u);
       tc_fence_after_sync();
       uint32_t ro[32];
@@ -1124,7 +1118,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       if (q_now) issue_next_q();
       const int sb = g & 1;
       const int key0 = (c_first + k * c_step) * CH3;
-      mbar_wait_a(bar_wg + BAR_S + (uint32_t)sb * 8u, (uint32_t)(g >> 1) & 1u);
+      mbar_wait_fast(bar_wg + BAR_S + (uint32_t)sb * 8u, (uint32_t)(g >> 1) & 1u);
       tc_fence_after_sync();
       float x[CH3];
       {
@@ -1203,7 +1197,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       const float nm = -m_run;
       const float es = plain ? sl2 : 1.0f;
       // P buffer sb was last read by P V of chunk g-2
-      if (g >= 2) mbar_wait_a(bar_wg + BAR_O + (uint32_t)sb * 8u, (uint32_t)((g - 2) >> 1) & 1u);
+      if (g >= 2) mbar_wait_fast(bar_wg + BAR_O + (uint32_t)sb * 8u, (uint32_t)((g - 2) >> 1) & 1u);
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
       const uint32_t p_dst = p_swz + (uint32_t)sb * SP3_BYTES;
 #pragma unroll
@@ -1213,15 +1207,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
         ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
         ffma2(x[j + 4], x[j + 5], x[j + 4], x[j + 5], es, es, nm, nm);
         ffma2(x[j + 6], x[j + 7], x[j + 6], x[j + 7], es, es, nm, nm);
-        if (!(a.dbg & 1)) {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
-        }
+        for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
-        if (!(a.dbg & 2))
         sts128(p_dst ^ ((uint32_t)cc << 4),
                pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
                pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
@@ -1230,10 +1221,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       if (q_now) complete_q(P + 1);
       // ---- a new pass overwrites O: the finished one has to leave TMEM first ----------------------
       if (k == 0 && g > 0) {
-        load_o(g - 1);
-        finish_pass(false);
+        float ot[DH];
+        load_o(g - 1, ot);
+        finish_pass(false, ot);
       }
-      if (!(a.dbg & 4)) fence_proxy_async_smem();
+      fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive_a(bar_wg + BAR_P + (uint32_t)sb * 8u);
       if (++k == n_uch) {
@@ -1241,9 +1233,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
         if (++pj == passes_per_tile) { pj = 0; q_tile += T; }
       }
     }
-    load_o(g - 1);
+    load_o(g - 1, o);
     if (pj == 0) q_tile -= T;                  // back to the tile of the last pass
-    finish_pass(true);
+    finish_pass(true, o);
+    } else {
+#pragma unroll
+      for (int d = 0; d < DH; ++d) o[d] = 0.f;  // nothing to do for this warpgroup: an empty partial
     }
 
     // ---- partials of a shared tile meet here ---------------------------------------------------
