@@ -32,6 +32,7 @@
 // (see include/cobevt_b200.h).
 #include "sm100.cuh"
 #include "common.h"
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through the runtime, libcuda is not linked)
 #include <cstring>
 #include <cstdlib>
 
@@ -57,8 +58,10 @@ struct KArgs {
   int32_t mode, sa, sb, resident_b;
   int32_t tiles_y, tiles_x, nslab;      // HALO geometry
   int32_t cin_log2, kw_magic;           // GATHER tap decode without divisions (cin_log2 < 0: generic)
+  int32_t use_tma;                      // A operand through TMA tensor loads (HALO / LINEAR) instead of per-thread cp.async
   int32_t dbg;                          // COBEVT_CONV_DEBUG bits (profiling experiments only): 1 no epilogue I/O, 2 no A loads, 4 no MMA
   uint32_t idesc;
+  alignas(64) CUtensorMap tmap;         // HALO: {C, W, H, N} box {64, 10, 18, 1}; LINEAR: {K, M} box {64, 128}; SWIZZLE_128B
 };
 
 // exact (erf) GELU of the reference (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26
@@ -111,6 +114,21 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32
       : "memory");
 }
 
+// TMA tensor loads (tile mode): the box lands at `smem_dst` in the tensor map's swizzle, out-of-bounds
+// elements are zero, completion is signalled as transaction bytes on `bar`.
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
 // output row (TMEM lane) -> linear output pixel index, or -1
 __device__ __forceinline__ int64_t out_row_index(const KArgs& a, int m_tile, int row) {
   const CobevtConvParams& p = a.p;
@@ -144,7 +162,7 @@ __device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&r)[U]) {
 }
 
 template <int BN>
-__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ KArgs a) {
   constexpr int kBStage = BN * BLOCK_K * 2;
   constexpr int NACC = BN >= 256 ? 2 : 4;         // accumulator buffers in TMEM (power of two)
   constexpr int kTmemCols = (NACC * BN) < 32 ? 32 : NACC * BN;
@@ -169,7 +187,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
 
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
-      mbar_init(&a_full[s], 128);
+      mbar_init(&a_full[s], a.use_tma ? 1 : 128);
       mbar_init(&a_empty[s], 1);
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
@@ -199,7 +217,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
     int ps = 0;        // stage of use `it`            (incremental: no runtime divisions in the loops)
     uint32_t pph = 1;  // parity to wait for on a_empty[ps]
     auto next_stage = [&]() { if (++ps == SA) { ps = 0; pph ^= 1u; } };
-    if (a.mode == MODE_LINEAR) {
+    if (a.use_tma) {
+      // One thread feeds the whole A ring: a 3-D halo box (conv padding = TMA out-of-bounds zero fill) or a
+      // 128-row token slab per stage, written by the TMA engine directly in the SWIZZLE_128B image the
+      // UMMA descriptors read.
+      if (tid == 0) {
+        const int per_img = a.tiles_y * a.tiles_x;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+          const int m_tile = tile / a.n_tiles;
+          if (a.mode == MODE_HALO) {
+            const int n = m_tile / per_img;
+            const int t = m_tile - n * per_img;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            for (int slab = 0; slab < a.nslab; ++slab) {
+              const int s = ps;
+              mbar_wait(&a_empty[s], pph);
+              next_stage();
+              mbar_arrive_expect_tx(&a_full[s], HALO_H * HALO_W * 128);
+              tma_load_4d(sA + s * A_HALO_BYTES, &a.tmap, &a_full[s], slab * 64, tx * TILE_W - 1, ty * TILE_H - 1, n);
+            }
+          } else {
+            for (int kb = 0; kb < KB; ++kb) {
+              const int s = ps;
+              mbar_wait(&a_empty[s], pph);
+              next_stage();
+              mbar_arrive_expect_tx(&a_full[s], A_GATHER_BYTES);
+              tma_load_2d(sA + s * A_GATHER_BYTES, &a.tmap, &a_full[s], kb * BLOCK_K, m_tile * BLOCK_M);
+            }
+          }
+        }
+      }
+    } else if (a.mode == MODE_LINEAR) {
       // 1x1 / stride 1: A rows are contiguous token rows, no coordinate arithmetic at all
       const int c8 = tid & 7, r0 = tid >> 3;
       const int64_t row_bytes = (int64_t)p.Cin * 2;
@@ -510,7 +558,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
     }
   } else if (warp == 13) {
     // ================================ MMA issuer ==========================================
-    if (lane == 0) {
+    // The whole warp walks the pipeline (waits, stage counters and descriptor arithmetic stay on the
+    // uniform datapath); one elected lane issues the tcgen05 instructions.
+    {
       uint32_t acc_it = 0;
       int sa_ = 0, sb_ = 0;            // current A / B stage and the parity to wait for
       uint32_t aph = 0, bph = 0;
@@ -520,6 +570,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
       const uint32_t lo0 = (uint32_t)tA_g;                 // LBO bits only (same for all three)
       const uint32_t hiA_g = (uint32_t)(tA_g >> 32), hiA_h = (uint32_t)(tA_h >> 32), hiB = hiA_g;
       const uint32_t idesc = a.idesc;
+      const bool do_mma = !(a.dbg & 4);
       if (a.resident_b) mbar_wait(&b_res_full, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
         const int buf = acc_it & (NACC - 1);
@@ -530,7 +581,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
         if (a.mode != MODE_HALO) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&a_full[sa_], aph);
-            fence_proxy_async_smem();     // cp.async (generic proxy) bytes -> visible to the UMMA (async proxy)
+            if (!a.use_tma) fence_proxy_async_smem();     // cp.async (generic proxy) bytes -> visible to the UMMA (async proxy)
             uint32_t sb_addr;
             if (a.resident_b) {
               sb_addr = smem_u32(sB + kb * kBStage);
@@ -541,46 +592,63 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
             tc_fence_after_sync();
             const uint32_t a_lo = lo0 | (smem_u32(sA + sa_ * A_GATHER_BYTES) >> 4);
             const uint32_t b_lo = lo0 | (sb_addr >> 4);
+            if (elect_one()) {
+              if (do_mma) {
 #pragma unroll
-            for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-              if (!(a.dbg & 4)) umma_lohi(d_tmem, a_lo + ks * 2, hiA_g, b_lo + ks * 2, hiB, idesc, accum);
-              accum = 1;
+                for (int ks = 0; ks < BLOCK_K / 16; ++ks) umma_lohi(d_tmem, a_lo + ks * 2, hiA_g, b_lo + ks * 2, hiB, idesc, (accum | ks) ? 1u : 0u);
+              }
+              umma_commit(&a_empty[sa_]);
+              if (!a.resident_b) umma_commit(&b_empty[sb_]);
             }
-            umma_commit(&a_empty[sa_]);
+            accum = 1;
             if (++sa_ == SA) { sa_ = 0; aph ^= 1u; }
-            if (!a.resident_b) { umma_commit(&b_empty[sb_]); if (++sb_ == SB) { sb_ = 0; bph ^= 1u; } }
+            if (!a.resident_b) { if (++sb_ == SB) { sb_ = 0; bph ^= 1u; } }
           }
         } else {
           const uint32_t tap_stride = (uint32_t)(a.nslab * kBStage) >> 4;     // resident B: next tap, same slab
           for (int slab = 0; slab < a.nslab; ++slab) {
             mbar_wait(&a_full[sa_], aph);
-            fence_proxy_async_smem();
+            if (!a.use_tma) fence_proxy_async_smem();
             tc_fence_after_sync();
             const uint32_t a_lo = lo0 | (smem_u32(sA + sa_ * A_HALO_BYTES) >> 4);
             uint32_t b_res_lo = lo0 | (smem_u32(sB + slab * kBStage) >> 4);
+            constexpr int kTapRows[9] = {0, 1, 2, HALO_W, HALO_W + 1, HALO_W + 2, 2 * HALO_W, 2 * HALO_W + 1, 2 * HALO_W + 2};
+            if (a.resident_b) {
+              if (elect_one()) {
+                if (do_mma) {
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              uint32_t b_lo = b_res_lo;
-              const int sb_cur = sb_;
-              if (!a.resident_b) {
+                  for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+                    for (int ks = 0; ks < BLOCK_K / 16; ++ks)
+                      umma_lohi(d_tmem, a_lo + kTapRows[tap] * 8 + ks * 2, hiA_h, b_res_lo + tap * tap_stride + ks * 2, hiB, idesc,
+                                (accum | tap | ks) ? 1u : 0u);
+                  }
+                }
+                umma_commit(&a_empty[sa_]);
+              }
+            } else {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
                 mbar_wait(&b_full[sb_], bph);
                 tc_fence_after_sync();
-                b_lo = lo0 | (smem_u32(sB + sb_ * kBStage) >> 4);
-              }
-              constexpr int kTapRows[9] = {0, 1, 2, HALO_W, HALO_W + 1, HALO_W + 2, 2 * HALO_W, 2 * HALO_W + 1, 2 * HALO_W + 2};
+                const uint32_t b_lo = lo0 | (smem_u32(sB + sb_ * kBStage) >> 4);
+                if (elect_one()) {
+                  if (do_mma) {
 #pragma unroll
-              for (int ks = 0; ks < BLOCK_K / 16; ++ks) {
-                if (!(a.dbg & 4)) umma_lohi(d_tmem, a_lo + kTapRows[tap] * 8 + ks * 2, hiA_h, b_lo + ks * 2, hiB, idesc, accum);
-                accum = 1;
+                    for (int ks = 0; ks < BLOCK_K / 16; ++ks)
+                      umma_lohi(d_tmem, a_lo + kTapRows[tap] * 8 + ks * 2, hiA_h, b_lo + ks * 2, hiB, idesc, (accum | tap | ks) ? 1u : 0u);
+                  }
+                  umma_commit(&b_empty[sb_]);
+                  if (tap == 8) umma_commit(&a_empty[sa_]);
+                }
+                if (++sb_ == SB) { sb_ = 0; bph ^= 1u; }
               }
-              if (!a.resident_b) { umma_commit(&b_empty[sb_cur]); if (++sb_ == SB) { sb_ = 0; bph ^= 1u; } }
-              b_res_lo += tap_stride;
             }
-            umma_commit(&a_empty[sa_]);
+            accum = 1;
             if (++sa_ == SA) { sa_ = 0; aph ^= 1u; }
           }
         }
-        umma_commit(&acc_full[buf]);
+        if (elect_one()) umma_commit(&acc_full[buf]);
       }
     }
   }
@@ -591,6 +659,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const KArgs a
 }
 
 int g_num_sms = 0;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// tensor map of the A operand for the TMA-fed modes; returns false if the layout cannot be described
+bool make_a_tmap(KArgs& a) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  const CobevtConvParams& p = a.p;
+  const CUtensorMapDataType dt = p.dtype == COBEVT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  CUresult r;
+  if (a.mode == MODE_HALO) {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Win * p.Cin * 2, (cuuint64_t)p.Hin * p.Win * p.Cin * 2};
+    const cuuint32_t box[4] = {64, HALO_W, HALO_H, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)a.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
+    const cuuint32_t box[2] = {BLOCK_K, BLOCK_M};
+    const cuuint32_t es[2] = {1, 1};
+    r = enc(&a.tmap, dt, 2, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  return r == CUDA_SUCCESS;
+}
 
 template <int BN>
 int launch(KArgs& a, cudaStream_t st) {
@@ -708,6 +817,13 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
     }
   }
   a.total_tiles = a.m_tiles * a.n_tiles;
+  {
+    static int no_tma = -1;
+    if (no_tma < 0) { const char* e = getenv("COBEVT_CONV_NOTMA"); no_tma = e ? atoi(e) : 0; }
+    a.use_tma = 0;
+    if (!no_tma && (a.mode == MODE_HALO || a.mode == MODE_LINEAR) && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0)
+      a.use_tma = make_a_tmap(a) ? 1 : 0;
+  }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->block_n) {
