@@ -45,9 +45,10 @@ constexpr int BLOCK_K = 64;
 constexpr int A_GATHER_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int HALO_H = 18, HALO_W = 10, TILE_H = 16, TILE_W = 8;
 constexpr int A_HALO_BYTES = 24 * 1024;                // 180 rows x 128 B = 23040, padded to 1 KB multiple
-constexpr int NUM_THREADS = 448;
+constexpr int NUM_THREADS = 640;                       // 20 warps, see the role table in conv_gemm_kernel
+constexpr int REGS_WORKERS = 104, REGS_CONTROL = 40;   // setmaxnreg split: 16 worker warps / loader + MMA warpgroup (pool 640 x 96)
 constexpr int SA_GATHER = 6, SA_HALO = 4;       // A ring depth (all stages may be in flight)
-constexpr int kMaxDynSmem = 227 * 1024 - 8192;         // static smem (barriers, bias, LN exchange) counts too
+constexpr int kMaxDynSmem = 227 * 1024 - 12288;        // static smem (barriers, bias, LN exchange) counts too
 constexpr int MAX_STAGES = 8;
 
 enum { MODE_GATHER = 0, MODE_HALO = 1, MODE_LINEAR = 2 };
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   __shared__ uint64_t acc_full[4], acc_empty[4], b_res_full;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sBias[512], sGamma[128], sBeta[128];
-  __shared__ float2 sXch[2][2][128];              // [tile parity][column half][row] = (mean, M2)
+  __shared__ float2 sXch[2][2][2][128];           // [team][tile parity][column half][row] = (mean, M2)
 
   const CobevtConvParams& p = a.p;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -210,44 +211,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s;
 
-  if (warp < 4) {
+  // ---- roles (20 warps) ------------------------------------------------------------------------
+  //   warps  4-11   epilogue team 0 (TMEM lane quarter = warp % 4, column half = (warp - 4) / 4)
+  //   warps  0- 3   A operand by TMA : epilogue team 1, column half 0  |  otherwise: cp.async A producers
+  //   warps 12-15   A operand by TMA : epilogue team 1, column half 1  |  otherwise: idle
+  //   warp  16      loader: weights (bulk copies) and, in the TMA modes, the A ring (tensor loads)
+  //   warp  17      MMA issuer            warps 18-19 idle (complete the control warpgroup for setmaxnreg)
+  // The two epilogue teams take alternate tiles (= alternate TMEM accumulators), so two epilogues are in
+  // flight: the epilogue of the token GEMMs is bound by per-warp latency, not by any pipe.
+  const int n_teams = a.use_tma ? 2 : 1;
+  int team = -1, e = 0;
+  if (warp >= 4 && warp < 12) { team = 0; e = warp - 4; }
+  else if (a.use_tma && warp < 4) { team = 1; e = warp; }
+  else if (a.use_tma && warp >= 12 && warp < 16) { team = 1; e = warp - 8; }
+
+  if (warp < 4 && !a.use_tma) {
     // ================================ A producers ========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKERS));
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
     uint32_t it = 0;   // stage uses issued so far (across tiles)
     int ps = 0;        // stage of use `it`            (incremental: no runtime divisions in the loops)
     uint32_t pph = 1;  // parity to wait for on a_empty[ps]
     auto next_stage = [&]() { if (++ps == SA) { ps = 0; pph ^= 1u; } };
-    if (a.use_tma) {
-      // One thread feeds the whole A ring: a 3-D halo box (conv padding = TMA out-of-bounds zero fill) or a
-      // 128-row token slab per stage, written by the TMA engine directly in the SWIZZLE_128B image the
-      // UMMA descriptors read.
-      if (tid == 0) {
-        const int per_img = a.tiles_y * a.tiles_x;
-        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
-          const int m_tile = tile / a.n_tiles;
-          if (a.mode == MODE_HALO) {
-            const int n = m_tile / per_img;
-            const int t = m_tile - n * per_img;
-            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
-            for (int slab = 0; slab < a.nslab; ++slab) {
-              const int s = ps;
-              mbar_wait(&a_empty[s], pph);
-              next_stage();
-              mbar_arrive_expect_tx(&a_full[s], HALO_H * HALO_W * 128);
-              tma_load_4d(sA + s * A_HALO_BYTES, &a.tmap, &a_full[s], slab * 64, tx * TILE_W - 1, ty * TILE_H - 1, n);
-            }
-          } else {
-            for (int kb = 0; kb < KB; ++kb) {
-              const int s = ps;
-              mbar_wait(&a_empty[s], pph);
-              next_stage();
-              mbar_arrive_expect_tx(&a_full[s], A_GATHER_BYTES);
-              tma_load_2d(sA + s * A_GATHER_BYTES, &a.tmap, &a_full[s], kb * BLOCK_K, m_tile * BLOCK_M);
-            }
-          }
-        }
-      }
-    } else if (a.mode == MODE_LINEAR) {
+    if (a.mode == MODE_LINEAR) {
       // 1x1 / stride 1: A rows are contiguous token rows, no coordinate arithmetic at all
       const int c8 = tid & 7, r0 = tid >> 3;
       const int64_t row_bytes = (int64_t)p.Cin * 2;
@@ -360,9 +346,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         }
       }
     }
-  } else if (warp < 12) {
-    // ================================ epilogue (8 warps) =================================
-    const int e = warp - 4;
+  } else if (team >= 0) {
+    // ================================ epilogue (8 warps per team) ==========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKERS));
     const int q4 = e & 3;             // TMEM lane quarter (== warp % 4)
     const int hf = e >> 2;            // column half
     const bool active = (BN >= 64) || (hf == 0);
@@ -374,6 +360,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const int m_tile = tile / a.n_tiles;
       const int n_tile = tile - m_tile * a.n_tiles;
       const int buf = acc_it & (NACC - 1);
+      if ((int)(acc_it % (uint32_t)n_teams) != team) continue;      // the other team's tile
       mbar_wait(&acc_full[buf], (acc_it / NACC) & 1);
       tc_fence_after_sync();
       if (!active) {
@@ -502,10 +489,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             for (int j = 0; j < U; ++j) { const float d = v[j] - mh; m2 += d * d; }
             float mean = mh, var = m2 * (1.0f / U);
             if constexpr (BN >= 64) {
-              const int par = acc_it & 1;   // exchange slots are double-buffered independently of NACC
-              sXch[par][hf][row] = make_float2(mh, m2);
-              asm volatile("bar.sync %0, 64;" ::"r"(q4 + 1) : "memory");
-              const float2 o = sXch[par][hf ^ 1][row];
+              const int par = (acc_it / (uint32_t)n_teams) & 1;   // exchange slots are double-buffered per team
+              sXch[team][par][hf][row] = make_float2(mh, m2);
+              asm volatile("bar.sync %0, 64;" ::"r"(1 + team * 4 + q4) : "memory");
+              const float2 o = sXch[team][par][hf ^ 1][row];
               mean = 0.5f * (mh + o.x);
               const float dlt = mh - o.x;
               var = (m2 + o.y + dlt * dlt * (float)(U / 2)) * (1.0f / (2 * U));
@@ -529,16 +516,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 12) {
-    // ================================ B loader (TMA bulk) ================================
+  } else if (warp == 16) {
+    // ================================ loader ==============================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
     if (lane == 0) {
       const uint8_t* wbase = reinterpret_cast<const uint8_t*>(p.w);
       if (a.resident_b) {
         mbar_arrive_expect_tx(&b_res_full, (uint32_t)(KB * kBStage));
         for (int kb = 0; kb < KB; ++kb) bulk_g2s(sB + kb * kBStage, wbase + (int64_t)kb * kBStage, kBStage, &b_res_full);
-      } else {
-        int bs = 0;
-        uint32_t bph = 1;
+      }
+      int bs = 0, ps = 0;                 // B / A ring positions and the parities to wait for
+      uint32_t bph = 1, pph = 1;
+      auto load_b = [&](const uint8_t* wb, int kb) {
+        mbar_wait(&b_empty[bs], bph);
+        mbar_arrive_expect_tx(&b_full[bs], kBStage);
+        bulk_g2s(sB + bs * kBStage, wb + (int64_t)kb * kBStage, kBStage, &b_full[bs]);
+        if (++bs == SB) { bs = 0; bph ^= 1u; }
+      };
+      if (a.use_tma) {
+        // One thread feeds both rings: the A stage is a 3-D halo box (conv padding = TMA out-of-bounds zero
+        // fill) or a 128-row token slab, written by the TMA engine directly in the SWIZZLE_128B image the
+        // UMMA descriptors read; the weight stages follow in the MMA's consumption order.
+        const int per_img = a.tiles_y * a.tiles_x;
+        for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+          const int m_tile = tile / a.n_tiles;
+          const int n_tile = tile - m_tile * a.n_tiles;
+          const uint8_t* wb = wbase + (int64_t)n_tile * KB * kBStage;
+          if (a.mode == MODE_HALO) {
+            const int n = m_tile / per_img;
+            const int t = m_tile - n * per_img;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            for (int slab = 0; slab < a.nslab; ++slab) {
+              mbar_wait(&a_empty[ps], pph);
+              mbar_arrive_expect_tx(&a_full[ps], HALO_H * HALO_W * 128);
+              tma_load_4d(sA + ps * A_HALO_BYTES, &a.tmap, &a_full[ps], slab * 64, tx * TILE_W - 1, ty * TILE_H - 1, n);
+              if (++ps == SA) { ps = 0; pph ^= 1u; }
+              if (!a.resident_b)
+                for (int tap = 0; tap < 9; ++tap) load_b(wb, tap * a.nslab + slab);
+            }
+          } else {
+            for (int kb = 0; kb < KB; ++kb) {
+              mbar_wait(&a_empty[ps], pph);
+              mbar_arrive_expect_tx(&a_full[ps], A_GATHER_BYTES);
+              tma_load_2d(sA + ps * A_GATHER_BYTES, &a.tmap, &a_full[ps], kb * BLOCK_K, m_tile * BLOCK_M);
+              if (++ps == SA) { ps = 0; pph ^= 1u; }
+              if (!a.resident_b) load_b(wb, kb);
+            }
+          }
+        }
+      } else if (!a.resident_b) {
         for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
           const int n_tile = tile % a.n_tiles;
           const uint8_t* wb = wbase + (int64_t)n_tile * KB * kBStage;
@@ -547,17 +573,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             // consumption order: GATHER kb = j; HALO (slab-major, taps inner) kb = tap*nslab + slab
             int kb = j;
             if (a.mode == MODE_HALO) { kb = tap * a.nslab + slab; if (++tap == 9) { tap = 0; ++slab; } }
-            const int s = bs;
-            mbar_wait(&b_empty[s], bph);
-            if (++bs == SB) { bs = 0; bph ^= 1u; }
-            mbar_arrive_expect_tx(&b_full[s], kBStage);
-            bulk_g2s(sB + s * kBStage, wb + (int64_t)kb * kBStage, kBStage, &b_full[s]);
+            load_b(wb, kb);
           }
         }
       }
     }
-  } else if (warp == 13) {
+  } else if (warp == 17) {
     // ================================ MMA issuer ==========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
     // The whole warp walks the pipeline (waits, stage counters and descriptor arithmetic stay on the
     // uniform datapath); one elected lane issues the tcgen05 instructions.
     {
@@ -651,6 +674,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         if (elect_one()) umma_commit(&acc_full[buf]);
       }
     }
+  } else if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));   // idle half of the control warpgroup
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKERS));   // warps 12-15 without a second team
   }
 
   tc_fence_before_sync();

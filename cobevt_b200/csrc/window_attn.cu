@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
       fence_proxy_async_smem();
       __syncthreads();
       // ---- S = Q K^T ----------------------------------------------------------
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(sQ);
         const uint32_t sb = smem_u32(sKV + buf * 2 * SK_BYTES);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
       tc_fence_before_sync();
       __syncthreads();
       // ---- O_c = P V -------------------------------------------------------------
-      if (tid == 0) {
+      if (warp == 0 && elect_one()) {
         tc_fence_after_sync();
         const uint32_t sa = smem_u32(sP);
         const uint32_t sv = smem_u32(sKV + buf * 2 * SK_BYTES + SK_BYTES);
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
     // registers (barrier F(k-2)); O(g) = P(g) V(g) follows the P(g) barrier.  The softmax threads hold
     // two chunks of logits in registers, so the issuer runs three chunks ahead of the exps.
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V2_REGS_ISSUER));
-    if (warp < 10 && (tid & 31) == 0 && total > 0) {
+    if (warp < 10 && total > 0) {     // whole warp walks the protocol, one elected lane issues
       const uint64_t dQK = make_smem_desc(0, 16, 512, LAYOUT_SW64);
       const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
       const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);
@@ -484,10 +484,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         }
         const uint32_t qa = q_addr + (Pq & q_dbuf) * (SQ_BYTES / 16);
         const uint32_t kb = k_addr + cq * (CH * 64 / 16);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks)
-          mma(tmem_base + (gq & 1) * CH, qk_lo | (qa + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
-        umma_commit(&bars[wg][gq & 1]);
+          for (int ks = 0; ks < DH / 16; ++ks)
+            mma(tmem_base + (gq & 1) * CH, qk_lo | (qa + ks * 2), qk_hi, qk_lo | (kb + ks * 2), qk_hi, a.idesc_qk, ks ? 1u : 0u);
+          umma_commit(&bars[wg][gq & 1]);
+        }
         ++gq;
         if (++cq == n_ch) { cq = 0; ++Pq; }
       };
@@ -500,10 +502,12 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AAr
         tc_fence_after_sync();
         {                                                           // O(g) = P(g) V(c)  -> O buffer g&1
           const uint32_t pa = p_addr + (g & 1) * (SP2_BYTES / 16), va = v_addr + c * (CH * 64 / 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < CH / 16; ++ks)
-            mma(tmem_base + 2 * CH + (g & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
-          umma_commit(&bars[wg][2 + (g & 1)]);
+            for (int ks = 0; ks < CH / 16; ++ks)
+              mma(tmem_base + 2 * CH + (g & 1) * DH, p_lo | (pa + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, ks ? 1u : 0u);
+            umma_commit(&bars[wg][2 + (g & 1)]);
+          }
         }
         if (gq < total) next_qk();
         if (++c == n_ch) c = 0;
@@ -939,7 +943,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
   if (is_mma) {
     // =============================== MMA issuer of warpgroup `wg` ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(V3_REGS_ISSUER));
-    if ((tid & 31) == 0 && total > 0) {
+    // the whole warp walks the protocol (waits, counters, descriptor arithmetic stay warp-uniform), one
+    // elected lane issues the tcgen05 instructions
+    if (total > 0) {
       const uint64_t dA = make_smem_desc(0, 16, 512, LAYOUT_SW64);      // Q, K, P: K-major 64-byte rows
       const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);     // V: MN-major
       const uint32_t a_lo = (uint32_t)dA, a_hi = (uint32_t)(dA >> 32);
@@ -963,10 +969,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
         }
         const uint32_t qa = q_addr + (Pq & 1) * (SQ_BYTES / 16);
         const uint32_t kb = k_addr + (c_first + kq * c_step) * (CH3 * 64 / 16);
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < DH / 16; ++ks)
-          mma(tmem_base + (gq & 1) * CH3, a_lo | (qa + ks * 2), a_hi, a_lo | (kb + ks * 2), a_hi, a.idesc_qk, ks ? 1u : 0u);
-        umma_commit(&bars[wg][gq & 1]);
+          for (int ks = 0; ks < DH / 16; ++ks)
+            mma(tmem_base + (gq & 1) * CH3, a_lo | (qa + ks * 2), a_hi, a_lo | (kb + ks * 2), a_hi, a.idesc_qk, ks ? 1u : 0u);
+          umma_commit(&bars[wg][gq & 1]);
+        }
         ++gq;
         if (++kq == n_uch) { kq = 0; ++Pq; }
       };
@@ -974,14 +982,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       if (total > 1) next_qk();
       int k = 0;
       for (int g = 0; g < total; ++g) {
-        mbar_wait(&bars[wg][4 + (g & 1)], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) and O(g-1) consumed
+        mbar_wait(&bars[wg][4 + (g & 1)], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) consumed
         tc_fence_after_sync();
-        {                                                           // O = P(g) V(chunk)
+        {                                                           // O (+)= P(g) V(chunk)
           const uint32_t pa = p_addr + (g & 1) * (SP3_BYTES / 16), va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
+          if (elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < CH3 / 16; ++ks)
-            mma(tmem_base + 2 * CH3, a_lo | (pa + ks * 2), a_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, (k | ks) ? 1u : 0u);
-          umma_commit(&bars[wg][2 + (g & 1)]);
+            for (int ks = 0; ks < CH3 / 16; ++ks)
+              mma(tmem_base + 2 * CH3, a_lo | (pa + ks * 2), a_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, (k | ks) ? 1u : 0u);
+            umma_commit(&bars[wg][2 + (g & 1)]);
+          }
         }
         if (gq < total) next_qk();
         if (++k == n_uch) k = 0;
