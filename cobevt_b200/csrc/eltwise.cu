@@ -2,6 +2,7 @@
 // one warp per token row where a row reduction is needed).  Each entry point cites the
 // reference lines it replaces; see include/cobevt_b200.h.
 #include "common.h"
+#include "sm100.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -343,6 +344,185 @@ __global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restri
   }
 }
 
+// ------------------------------------------------------------------ grouped-lane variants
+// LPC lanes share one cell (CPL consecutive channels each, a 16- or 32-byte vector), so a warp handles
+// 32 / LPC cells per instruction and the three row reductions are log2(LPC) shuffle steps instead of 5.
+// These are the versions the entry points launch; the one-warp-per-cell kernels above remain for C
+// values the grouped mapping does not cover.
+template <int LPC>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// vector q of a lane covers channels q * (LPC * 8) + grp * 8 .. + 8: every warp-wide 16-byte access then
+// touches whole 128-byte lines
+template <int CPL, int LPC>
+__device__ __forceinline__ int chan_of(int grp, int i) { return (i >> 3) * (LPC * 8) + grp * 8 + (i & 7); }
+template <int CPL, int LPC>
+__device__ __forceinline__ void load_vec(const uint16_t* row, int grp, int bf16, float (&v)[CPL]) {
+#pragma unroll
+  for (int q = 0; q < CPL / 8; ++q) {
+    const uint4 u = *reinterpret_cast<const uint4*>(row + q * (LPC * 8) + grp * 8);
+    const float2 a = up2(u.x, bf16), b = up2(u.y, bf16), c = up2(u.z, bf16), d = up2(u.w, bf16);
+    v[q * 8 + 0] = a.x; v[q * 8 + 1] = a.y; v[q * 8 + 2] = b.x; v[q * 8 + 3] = b.y;
+    v[q * 8 + 4] = c.x; v[q * 8 + 5] = c.y; v[q * 8 + 6] = d.x; v[q * 8 + 7] = d.y;
+  }
+}
+template <int CPL, int LPC>
+__device__ __forceinline__ void store_vec(uint16_t* row, int grp, int bf16, const float (&v)[CPL]) {
+#pragma unroll
+  for (int q = 0; q < CPL / 8; ++q) {
+    uint4 u;
+    u.x = pk2(v[q * 8 + 0], v[q * 8 + 1], bf16); u.y = pk2(v[q * 8 + 2], v[q * 8 + 3], bf16);
+    u.z = pk2(v[q * 8 + 4], v[q * 8 + 5], bf16); u.w = pk2(v[q * 8 + 6], v[q * 8 + 7], bf16);
+    *reinterpret_cast<uint4*>(row + q * (LPC * 8) + grp * 8) = u;
+  }
+}
+
+template <int CPL, int LPC>
+__global__ void __launch_bounds__(256) ray_embed_grouped_kernel(const float* __restrict__ I_inv, const float* __restrict__ E_inv,
+                                 const float* __restrict__ w_img, const float* __restrict__ w_cam,
+                                 uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
+                                 int invert_I, int bf16, int cpb) {
+  constexpr int C = CPL * LPC, CPW = 32 / LPC;          // channels, cells per warp and step
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane % LPC, sub = lane / LPC;         // channel group, cell slot inside the warp
+  const int v = blockIdx.y;
+  float Ii[9];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) Ii[r] = I_inv[v * 9 + r];
+  if (invert_I) {   // batch['intrinsic'].inverse(), fax_modules.py:500-501 (adjugate / determinant)
+    const float a = Ii[0], b_ = Ii[1], c_ = Ii[2], d_ = Ii[3], e_ = Ii[4], f = Ii[5], g = Ii[6], hh = Ii[7], k = Ii[8];
+    const float A = e_ * k - f * hh, B = -(d_ * k - f * g), Cc = d_ * hh - e_ * g;
+    const float idet = 1.0f / (a * A + b_ * B + c_ * Cc);
+    Ii[0] = A * idet;  Ii[1] = -(b_ * k - c_ * hh) * idet; Ii[2] = (b_ * f - c_ * e_) * idet;
+    Ii[3] = B * idet;  Ii[4] = (a * k - c_ * g) * idet;    Ii[5] = -(a * f - c_ * d_) * idet;
+    Ii[6] = Cc * idet; Ii[7] = -(a * hh - b_ * g) * idet;  Ii[8] = (a * e_ - b_ * d_) * idet;
+  }
+  // pixel -> ray direction is affine: d = M3 (px, py, 1) with M3 = E_inv[:, :3] I_inv (4 x 3) plus E_inv[:, 3]
+  float M[4][3];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float e0 = E_inv[v * 16 + r * 4], e1 = E_inv[v * 16 + r * 4 + 1], e2 = E_inv[v * 16 + r * 4 + 2], e3 = E_inv[v * 16 + r * 4 + 3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) M[r][c] = e0 * Ii[c] + e1 * Ii[3 + c] + e2 * Ii[6 + c];
+    M[r][2] += e3;
+  }
+  // per-channel: a = wi . d - ce  ->  a = A0 px + A1 py + A2   (3 FMAs per element instead of 16 + 4)
+  float A0[CPL], A1[CPL], A2[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = chan_of<CPL, LPC>(grp, i);
+    const float w0 = w_img[ch * 4], w1 = w_img[ch * 4 + 1], w2 = w_img[ch * 4 + 2], w3 = w_img[ch * 4 + 3];
+    float cacc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) cacc += w_cam[ch * 4 + r] * E_inv[v * 16 + r * 4 + 3];
+    A0[i] = w0 * M[0][0] + w1 * M[1][0] + w2 * M[2][0] + w3 * M[3][0];
+    A1[i] = w0 * M[0][1] + w1 * M[1][1] + w2 * M[2][1] + w3 * M[3][1];
+    A2[i] = w0 * M[0][2] + w1 * M[1][2] + w2 * M[2][2] + w3 * M[3][2] - cacc;
+  }
+  const int ncell = h * w;
+  const int base = blockIdx.x * cpb;
+  const float sx = w > 1 ? image_w / (float)(w - 1) : 0.f, sy = h > 1 ? image_h / (float)(h - 1) : 0.f;
+  for (int cc = warp * CPW + sub; cc < cpb; cc += 8 * CPW) {
+    const int cell = base + cc;
+    const int cl = cell < ncell ? cell : ncell - 1;
+    const int iy = cl / w, ix = cl - iy * w;
+    const float px = (float)ix * sx, py = (float)iy * sy;
+    float e[CPL];
+    float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) {
+      sm100::ffma2(e[i], e[i + 1], A1[i], A1[i + 1], py, py, A2[i], A2[i + 1]);
+      sm100::ffma2(e[i], e[i + 1], A0[i], A0[i + 1], px, px, e[i], e[i + 1]);
+      sm100::ffma2(ss0, ss1, e[i], e[i + 1], e[i], e[i + 1], ss0, ss1);
+    }
+    const float ss = group_sum<LPC>(ss0 + ss1);
+    const float inv = __fdividef(1.0f, sqrtf(ss) + 1e-7f);
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) sm100::fmul2(e[i], e[i + 1], e[i], e[i + 1], inv, inv);
+    if (cell < ncell) store_vec<CPL, LPC>(out + ((int64_t)v * ncell + cell) * C, grp, bf16, e);
+  }
+}
+
+template <int CPL, int LPC>
+__global__ void __launch_bounds__(256) bev_query_grouped_kernel(const uint16_t* __restrict__ x, int64_t x_rows, const float* __restrict__ world,
+                                 const float* __restrict__ w_bev, const float* __restrict__ b_bev,
+                                 const float* __restrict__ w_cam, const float* __restrict__ E_inv,
+                                 uint16_t* __restrict__ out, int n, int P, float eps, int bf16, int cpb) {
+  constexpr int C = CPL * LPC, CPW = 32 / LPC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int grp = lane % LPC, sub = lane / LPC;
+  const int v = blockIdx.y;
+  const int b = v / n;
+  const float* Ei = E_inv + (int64_t)v * 16;
+  const float c0 = Ei[3], c1 = Ei[7], c2 = Ei[11], c3 = Ei[15];
+  float wb0[CPL], wb1[CPL], ce[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    const int ch = chan_of<CPL, LPC>(grp, i);
+    wb0[i] = w_bev[ch * 2];
+    wb1[i] = w_bev[ch * 2 + 1];
+    ce[i] = b_bev[ch] - (w_cam[ch * 4] * c0 + w_cam[ch * 4 + 1] * c1 + w_cam[ch * 4 + 2] * c2 + w_cam[ch * 4 + 3] * c3);
+  }
+  const int base = blockIdx.x * cpb;
+  constexpr float invC = 1.0f / (float)C;
+  // the loads of the next cell are issued before the reductions of the current one (register prefetch)
+  const int64_t xbase = (x_rows == (int64_t)P) ? 0 : (int64_t)b * P;   // broadcast prior or per-row map
+  uint4 xn[CPL / 8];
+  float wxn, wyn;
+  auto fetch = [&](int cc) {
+    const int cell = base + cc;
+    const int pp = cell < P ? cell : P - 1;
+    wxn = world[pp]; wyn = world[P + pp];
+    const uint16_t* row = x + (xbase + pp) * C;
+#pragma unroll
+    for (int q = 0; q < CPL / 8; ++q) xn[q] = *reinterpret_cast<const uint4*>(row + q * (LPC * 8) + grp * 8);
+  };
+  fetch(warp * CPW + sub);
+  for (int cc = warp * CPW + sub; cc < cpb; cc += 8 * CPW) {
+    const int cell = base + cc;
+    const float wx = wxn, wy = wyn;
+    float xv[CPL], e[CPL];
+#pragma unroll
+    for (int q = 0; q < CPL / 8; ++q) {
+      const float2 a = up2(xn[q].x, bf16), b2 = up2(xn[q].y, bf16), c = up2(xn[q].z, bf16), d = up2(xn[q].w, bf16);
+      xv[q * 8 + 0] = a.x; xv[q * 8 + 1] = a.y; xv[q * 8 + 2] = b2.x; xv[q * 8 + 3] = b2.y;
+      xv[q * 8 + 4] = c.x; xv[q * 8 + 5] = c.y; xv[q * 8 + 6] = d.x; xv[q * 8 + 7] = d.y;
+    }
+    if (cc + 8 * CPW < cpb) fetch(cc + 8 * CPW);
+    // packed fp32 pairs: 4 issue slots per element for the whole chain
+    float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) {
+      sm100::ffma2(e[i], e[i + 1], wb1[i], wb1[i + 1], wy, wy, ce[i], ce[i + 1]);
+      sm100::ffma2(e[i], e[i + 1], wb0[i], wb0[i + 1], wx, wx, e[i], e[i + 1]);
+      sm100::ffma2(ss0, ss1, e[i], e[i + 1], e[i], e[i + 1], ss0, ss1);
+    }
+    const float ss = group_sum<LPC>(ss0 + ss1);
+    const float inv = __fdividef(1.0f, sqrtf(ss) + 1e-7f);
+    float s10 = 0.f, s11 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) {
+      sm100::ffma2(e[i], e[i + 1], e[i], e[i + 1], inv, inv, xv[i], xv[i + 1]);
+      sm100::fadd2(s10, s11, s10, s11, e[i], e[i + 1]);
+    }
+    const float mean = group_sum<LPC>(s10 + s11) * invC;
+    const float nmean = -mean;
+    float s20 = 0.f, s21 = 0.f;
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) {
+      sm100::fadd2(e[i], e[i + 1], e[i], e[i + 1], nmean, nmean);
+      sm100::ffma2(s20, s21, e[i], e[i + 1], e[i], e[i + 1], s20, s21);
+    }
+    const float rstd = rsqrtf(group_sum<LPC>(s20 + s21) * invC + eps);
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) sm100::fmul2(e[i], e[i + 1], e[i], e[i + 1], rstd, rstd);
+    if (cell < P) store_vec<CPL, LPC>(out + ((int64_t)v * P + cell) * C, grp, bf16, e);
+  }
+}
+
 // ------------------------------------------------------------------ LayerNorm over rows
 __global__ void layernorm_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint16_t* __restrict__ y, int64_t rows, int C,
@@ -632,12 +812,28 @@ extern "C" int cobevt_bn_relu2(const void* x, const float* sa, const float* ba, 
   return cobevt::check_launch("bn_relu2");
 }
 
+// cells per block of the grouped kernels: the per-block set-up (embedding weights into registers) is ~100 loads
+// per thread, so blocks are made as long as a grid of ~6 blocks per SM allows
+static int cells_per_block(int64_t ncell, int views) {
+  int64_t cpb = (ncell * views + 148 * 6 - 1) / (148 * 6);
+  cpb = (cpb + 255) / 256 * 256;
+  if (cpb < 256) cpb = 256;
+  if (cpb > 8192) cpb = 8192;
+  return (int)cpb;
+}
+
 extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const float* w_img, const float* w_cam, void* out,
                                  int32_t NV, int32_t h, int32_t w, float image_h, float image_w, int32_t C,
                                  int32_t invert_intrinsic, int32_t dtype, void* stream) {
   if (!I_inv || !E_inv || !w_img || !w_cam || !out || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "ray_embed: bad args (C must be 64/128/256)");
+  const int cpb = cells_per_block((int64_t)h * w, NV);
+  dim3 gridg((h * w + cpb - 1) / cpb, NV);
   dim3 grid((h * w + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, NV);
-  if (C == 128) ray_embed_kernel<4><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  if (C == 128) ray_embed_grouped_kernel<16, 8><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 64) ray_embed_grouped_kernel<8, 8><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 32) ray_embed_grouped_kernel<8, 4><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 256) ray_embed_grouped_kernel<16, 16><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 128) ray_embed_kernel<4><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   else if (C == 32) ray_embed_kernel<1><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   else if (C == 64) ray_embed_kernel<2><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   else ray_embed_kernel<8><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
@@ -649,8 +845,14 @@ extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* worl
                                  int32_t C, float eps, int32_t dtype, void* stream) {
   if (!x || !world || !w_bev || !b_bev || !w_cam || !E_inv || !out || !ok_c(C) || x_rows <= 0)
     return fail(COBEVT_ERR_SHAPE, "bev_query: bad args");
+  const int cpb = cells_per_block(P, BL * n);
+  dim3 gridg((P + cpb - 1) / cpb, BL * n);
   dim3 grid((P + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, BL * n);
-  if (C == 128) bev_query_kernel<4><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  if (C == 128) bev_query_grouped_kernel<16, 8><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 64) bev_query_grouped_kernel<8, 8><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 32) bev_query_grouped_kernel<8, 4><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 256) bev_query_grouped_kernel<16, 16><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 128) bev_query_kernel<4><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   else if (C == 32) bev_query_kernel<1><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   else if (C == 64) bev_query_kernel<2><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   else bev_query_kernel<8><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
