@@ -1,6 +1,7 @@
 // Host-side helpers shared by the C-ABI translation units.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda.h>          // CUtensorMap (the encoder is fetched through the runtime, libcuda is not linked)
 #include <cstdio>
 #include <cstdarg>
 #include "../../include/cobevt_b200.h"
@@ -24,5 +25,22 @@ inline int check_launch(const char* what) {
 }
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point table (nullptr if unavailable)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
 
 }  // namespace cobevt

@@ -39,6 +39,8 @@ struct AArgs {
   int32_t dbg;   // COBEVT_ATTN_DEBUG (timing experiments only; results are wrong): 1 no MUFU, 2 no P stores, 4 no proxy fence, 8 second warpgroup idle
   int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
   uint32_t idesc_qk, idesc_pv;
+  int32_t kv_tma;                     // resident K / V windows are fetched by two 4-D TMA tensor loads
+  alignas(64) CUtensorMap tmK, tmV;   // {C, Wv, Hv, B*views}, box {32, w2 (span), w1 (span), views}, SWIZZLE_64B
 };
 
 struct Tok {
@@ -80,7 +82,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int bf16) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-__global__ void __launch_bounds__(128, 2) window_attn_kernel(const AArgs a) {
+__global__ void __launch_bounds__(128, 2) window_attn_kernel(const __grid_constant__ AArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -361,7 +363,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // boundaries (the next pass' Q tile is prefetched into a second buffer while the current one is
 // being processed), so the softmax threads never see a pipeline refill.
 template <bool BF16>
-__global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const AArgs a) {
+__global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __grid_constant__ AArgs a) {
   // roles: warps 0-3 = softmax group 0, warps 4-7 = softmax group 1, warp 8 / 9 lane 0 = their MMA issuers
   // (warps 10, 11 only exist so that the issuers form a full warpgroup for setmaxnreg)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -846,7 +848,7 @@ constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 8 KB per P buffer
 __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + 2 * SP3_BYTES); }
 
 template <bool BF16>
-__global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AArgs a) {
+__global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __grid_constant__ AArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_ch = (a.Lk + CH3 - 1) / CH3;
@@ -858,6 +860,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
   __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S0 S1 | O0 O1 | P0 P1 | Q0 Q1
   enum : uint32_t { BAR_S = 0, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
+  __shared__ __align__(8) uint64_t bar_kv;                  // K / V windows landed (TMA path)
   __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
   __shared__ uint32_t tmem_base_s;
 
@@ -877,7 +880,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
       for (int j = 0; j < 2; ++j) {
         mbar_init(&bars[i][j], 1); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
       }
+    mbar_init(&bar_kv, 1);
     mbar_fence_init();
+    if (a.kv_tma) {
+      // the whole key window of every view is one strided box: 2 instructions instead of 16 B per thread
+      const int X = win / a.k_ny, Y = win - X * a.k_ny;
+      const int c1 = p.kvmap.grid ? Y : Y * p.kvmap.w2, c2 = p.kvmap.grid ? X : X * p.kvmap.w1;
+      mbar_arrive_expect_tx(&bar_kv, (uint32_t)a.Lk * 128u);
+      tma_load_4d(sK, &a.tmK, &bar_kv, head * DH, c1, c2, b * p.kvmap.views);
+      tma_load_4d(sV, &a.tmV, &bar_kv, head * DH, c1, c2, b * p.kvmap.views);
+    }
   }
   if (warp == 0) {
     tmem_alloc(&tmem_base_s, 512);
@@ -887,7 +899,25 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
   const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
   const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
 
-  // ---- resident K / V: 4 lanes per token (64 contiguous bytes), all threads -----------------
+  if (a.kv_tma) {
+    // key mask vector + zero rows behind the window (their P is 0, but 0 x garbage could be NaN)
+    for (int tok = tid; tok < keys_pad; tok += V3_THREADS) {
+      float km = 0.f;
+      if (tok >= a.Lk) {
+        km = -INFINITY;
+#pragma unroll
+        for (int piece = 0; piece < 4; ++piece) {
+          *reinterpret_cast<uint4*>(sK + sw64_off(tok, piece)) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(sV + sw64_off(tok, piece)) = make_uint4(0, 0, 0, 0);
+        }
+      } else if (p.key_mask) {
+        const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, tok);
+        if (p.key_mask[(((int64_t)b * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kvmap.views + t.n] == 0) km = -INFINITY;
+      }
+      kmask[tok] = km;
+    }
+  } else
+  // ---- resident K / V by cp.async: 4 lanes per token (64 contiguous bytes), all threads --------
   for (int idx = tid; idx < keys_pad * 4; idx += V3_THREADS) {
     const int tok = idx >> 2, piece = idx & 3;
     const uint8_t* srcK = kb_;
@@ -961,6 +991,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const AAr
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
             ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
       };
+      if (a.kv_tma) mbar_wait(&bar_kv, 0);
       int gq = 0, Pq = 0, kq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
       auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T  -> S buffer gq&1
         if (kq == 0) {
@@ -1333,6 +1364,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   AArgs a;
   a.p = *p;
   a.q_dbuf = 0;
+  a.kv_tma = 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   a.q_nx = qm.H / qm.w1; a.q_ny = qm.W / qm.w2;
   a.k_nx = km.H / km.w1; a.k_ny = km.W / km.w2;
@@ -1373,6 +1405,28 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
       }
       a.q_dbuf = 1;
       a.idesc_qk = make_idesc_f16(128, CH3, bf, false, false);
+      {
+        static int no_tma = -1;
+        if (no_tma < 0) { const char* e = getenv("COBEVT_ATTN_NOTMA"); no_tma = e ? atoi(e) : 0; }
+        a.kv_tma = 0;
+        const int sx = km.grid ? a.k_nx : 1, sy = km.grid ? a.k_ny : 1;      // traversal strides along H / W
+        const int span_h = (km.w1 - 1) * sx + 1, span_w = (km.w2 - 1) * sy + 1;
+        cobevt::EncodeTiledFn enc = cobevt::get_encode_tiled();
+        if (!no_tma && enc && km.Hv == km.H && km.Wv == km.W && sx <= 8 && sy <= 8 && span_h <= 256 && span_w <= 256 &&
+            km.views <= 256 && ((reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v)) & 15) == 0) {
+          const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+          const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)km.Wv, (cuuint64_t)km.Hv, (cuuint64_t)p->B * km.views};
+          const cuuint64_t strides[3] = {(cuuint64_t)a.p.kv_stride * 2, (cuuint64_t)km.Wv * a.p.kv_stride * 2,
+                                         (cuuint64_t)km.Hv * km.Wv * a.p.kv_stride * 2};
+          const cuuint32_t box[4] = {DH, (cuuint32_t)span_w, (cuuint32_t)span_h, (cuuint32_t)km.views};
+          const cuuint32_t es[4] = {1, (cuuint32_t)sy, (cuuint32_t)sx, 1};
+          const CUresult r1 = enc(&a.tmK, dt, 4, const_cast<void*>(p->k), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          const CUresult r2 = enc(&a.tmV, dt, 4, const_cast<void*>(p->v), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+          a.kv_tma = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 1 : 0;
+        }
+      }
       const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
       kern<<<(unsigned)ctas, V3_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
       return cobevt::check_launch("window_attn_v3_kernel");
