@@ -837,15 +837,16 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
 //   * 1 or 2 query tiles: the G = 4 / tiles warpgroups that share a tile split its passes (mean over
 //     query views: partial means add up) or, with a single pass, its key chunks (independent online
 //     softmax streams, log-sum-exp merge); the partials meet once, at the end, through shared memory.
-// TMEM per warpgroup (128 columns): S0 [0,32) S1 [32,64) O [64,96) ACC [96,128).  O accumulates in TMEM over
+// TMEM per warpgroup (128 columns): S [0,64) O [64,96) ACC [96,128); S and the P tile in shared memory are
+// single-buffered -- the other three warpgroups cover the tensor-core round trips.  O accumulates in TMEM over
 // the chunks of a pass (lazy rescale, see below): no tensor-core round trip sits on the per-chunk path.
 // =====================================================================================
-constexpr int CH3 = 32;                                  // keys per chunk
+constexpr int CH3 = 64;                                  // keys per chunk
 constexpr int V3_WG = 4;
 constexpr int V3_THREADS = (V3_WG + 1) * 128;            // 640
 constexpr int V3_REGS_SOFTMAX = 112, V3_REGS_ISSUER = 32;   // the CTA pool is 640 x 96 = 61440 = 16*32*112 + 4*32*32
-constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 8 KB per P buffer
-__host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + 2 * SP3_BYTES); }
+constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 16 KB: one P buffer per warpgroup
+__host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + SP3_BYTES); }
 
 template <bool BF16>
 __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __grid_constant__ AArgs a) {
@@ -854,12 +855,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   const int n_ch = (a.Lk + CH3 - 1) / CH3;
   const int keys_pad = n_ch * CH3;
   uint8_t* sQ_all = smem;                                   // per warpgroup: 2 x 8 KB
-  uint8_t* sP_all = sQ_all + V3_WG * 2 * SQ_BYTES;          // per warpgroup: 2 x 8 KB (also the merge scratch)
-  uint8_t* sK = sP_all + V3_WG * 2 * SP3_BYTES;
+  uint8_t* sP_all = sQ_all + V3_WG * 2 * SQ_BYTES;          // per warpgroup: 16 KB (also the merge scratch)
+  uint8_t* sK = sP_all + V3_WG * SP3_BYTES;
   uint8_t* sV = sK + keys_pad * 64;
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
-  __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S0 S1 | O0 O1 | P0 P1 | Q0 Q1
-  enum : uint32_t { BAR_S = 0, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
+  __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S F | O - | P - | Q0 Q1
+  enum : uint32_t { BAR_S = 0, BAR_F = 8, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
   __shared__ __align__(8) uint64_t bar_kv;                  // K / V windows landed (TMA path)
   __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
   __shared__ uint32_t tmem_base_s;
@@ -878,7 +879,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     for (int i = 0; i < V3_WG; ++i)
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        mbar_init(&bars[i][j], 1); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
+        mbar_init(&bars[i][j], j == 0 ? 1 : 128); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
       }
     mbar_init(&bar_kv, 1);
     mbar_fence_init();
@@ -954,7 +955,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_s + wg * 128;
   uint8_t* sQ = sQ_all + wg * 2 * SQ_BYTES;
-  uint8_t* sP = sP_all + wg * 2 * SP3_BYTES;
+  uint8_t* sP = sP_all + wg * SP3_BYTES;
   const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
 
   // ---- work split ---------------------------------------------------------------------------
@@ -976,9 +977,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     // the whole warp walks the protocol (waits, counters, descriptor arithmetic stay warp-uniform), one
     // elected lane issues the tcgen05 instructions
     if (total > 0) {
-      const uint64_t dA = make_smem_desc(0, 16, 512, LAYOUT_SW64);      // Q, K, P: K-major 64-byte rows
+      const uint64_t dA = make_smem_desc(0, 16, 512, LAYOUT_SW64);      // Q, K: K-major 64-byte rows
+      const uint64_t dP = make_smem_desc(0, 16, 1024, LAYOUT_SW128);    // P: K-major 128-byte rows
       const uint64_t dV = make_smem_desc(0, 512, 512, LAYOUT_SW64);     // V: MN-major
       const uint32_t a_lo = (uint32_t)dA, a_hi = (uint32_t)(dA >> 32);
+      const uint32_t p_lo = (uint32_t)dP, p_hi = (uint32_t)(dP >> 32);
       const uint32_t v_lo = (uint32_t)dV, v_hi = (uint32_t)(dV >> 32);
       const uint32_t q_addr = smem_u32(sQ) >> 4, k_addr = smem_u32(sK) >> 4, v_addr = smem_u32(sV) >> 4;
       const uint32_t p_addr = smem_u32(sP) >> 4;
@@ -993,7 +996,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       };
       if (a.kv_tma) mbar_wait(&bar_kv, 0);
       int gq = 0, Pq = 0, kq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
-      auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T  -> S buffer gq&1
+      auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T
         if (kq == 0) {
           mbar_wait(&bars[wg][6 + (Pq & 1)], (uint32_t)(Pq >> 1) & 1u);
           tc_fence_after_sync();
@@ -1003,28 +1006,31 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
-            mma(tmem_base + (gq & 1) * CH3, a_lo | (qa + ks * 2), a_hi, a_lo | (kb + ks * 2), a_hi, a.idesc_qk, ks ? 1u : 0u);
-          umma_commit(&bars[wg][gq & 1]);
+            mma(tmem_base, a_lo | (qa + ks * 2), a_hi, a_lo | (kb + ks * 2), a_hi, a.idesc_qk, ks ? 1u : 0u);
+          umma_commit(&bars[wg][0]);
         }
         ++gq;
         if (++kq == n_uch) { kq = 0; ++Pq; }
       };
       next_qk();
-      if (total > 1) next_qk();
       int k = 0;
       for (int g = 0; g < total; ++g) {
-        mbar_wait(&bars[wg][4 + (g & 1)], (uint32_t)(g >> 1) & 1u);     // P(g) written, S(g) consumed
+        if (gq < total) {                   // S(g) has left TMEM: S(g+1) may overwrite it
+          mbar_wait(&bars[wg][1], (uint32_t)g & 1u);
+          tc_fence_after_sync();
+          next_qk();
+        }
+        mbar_wait(&bars[wg][4], (uint32_t)g & 1u);                  // P(g) written
         tc_fence_after_sync();
         {                                                           // O (+)= P(g) V(chunk)
-          const uint32_t pa = p_addr + (g & 1) * (SP3_BYTES / 16), va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
+          const uint32_t va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < CH3 / 16; ++ks)
-              mma(tmem_base + 2 * CH3, a_lo | (pa + ks * 2), a_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, (k | ks) ? 1u : 0u);
-            umma_commit(&bars[wg][2 + (g & 1)]);
+              mma(tmem_base + CH3, p_lo | (p_addr + ks * 2), p_hi, v_lo | (va + ks * 64), v_hi, a.idesc_pv, (k | ks) ? 1u : 0u);
+            umma_commit(&bars[wg][2]);
           }
         }
-        if (gq < total) next_qk();
         if (++k == n_uch) k = 0;
       }
     }
@@ -1032,12 +1038,12 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(V3_REGS_SOFTMAX));
     // =============================== softmax warpgroup `wg` ==================================
     const uint32_t t_row = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    const uint32_t t_o = t_row + 2 * CH3, t_acc = t_row + 2 * CH3 + DH;
+    const uint32_t t_o = t_row + CH3, t_acc = t_row + CH3 + DH;
     const float sl2 = p.scale * 1.4426950408889634f;
     const float L2E = 1.4426950408889634f;
     const bool any_mask = p.key_mask != nullptr;
     const bool bias_vec = (a.Lk & 3) == 0;
-    const uint32_t p_swz = (smem_u32(sP) + (uint32_t)wtid * 64u) | ((((uint32_t)wtid >> 1) & 3u) << 4);   // SW64 row
+    const uint32_t p_swz = (smem_u32(sP) + (uint32_t)wtid * 128u) | (((uint32_t)wtid & 7u) << 4);          // SW128 row
     const uint32_t bar_wg = smem_u32(&bars[wg][0]);
     const uint32_t km_s = smem_u32(kmask);
     const float inv_passes = 1.0f / (float)a.q_passes;
@@ -1142,7 +1148,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     };
     // the finished pass' O: TMEM -> o
     auto load_o = [&](int glast, float (&o)[DH]) {
-      mbar_wait_a(bar_wg + BAR_O + (uint32_t)(glast & 1) * 8u, (uint32_t)(glast >> 1) & 1u);
+      mbar_wait_a(bar_wg + BAR_O, (uint32_t)glast & 1u);
       tc_fence_after_sync();
       uint32_t ro[32];
       tmem_ld_32x32b_x32(t_o, ro);
@@ -1157,18 +1163,20 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     for (; g < total; ++g) {
       const bool q_now = (k == 0) && (P + 1 < NP);
       if (q_now) issue_next_q();
-      const int sb = g & 1;
       const int key0 = (c_first + k * c_step) * CH3;
-      mbar_wait_fast(bar_wg + BAR_S + (uint32_t)sb * 8u, (uint32_t)(g >> 1) & 1u);
+      mbar_wait_fast(bar_wg + BAR_S, (uint32_t)g & 1u);
       tc_fence_after_sync();
       float x[CH3];
       {
-        uint32_t r0[32];
-        tmem_ld_32x32b_x32(t_row + sb * CH3, r0);
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_row, r0);
+        tmem_ld_32x32b_x32(t_row + 32, r1);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < CH3; ++j) x[j] = __uint_as_float(r0[j]);
+        for (int j = 0; j < 32; ++j) { x[j] = __uint_as_float(r0[j]); x[32 + j] = __uint_as_float(r1[j]); }
       }
+      tc_fence_before_sync();
+      mbar_arrive_a(bar_wg + BAR_F);                // S(g) sits in registers: its TMEM columns are free
       const bool use_km = any_mask || (key0 + CH3 > a.Lk);
       const bool plain = !use_km && !(p.bias != nullptr);
       float cmax;                                   // chunk max, log2 domain
@@ -1223,7 +1231,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           if (grow) m_run = cmax;
           l_run *= fac;
           // every P V issued so far (chunks <= g-1) must have landed before O is touched
-          mbar_wait_a(bar_wg + BAR_O + (uint32_t)((g - 1) & 1) * 8u, (uint32_t)((g - 1) >> 1) & 1u);
+          mbar_wait_a(bar_wg + BAR_O, (uint32_t)(g - 1) & 1u);
           tc_fence_after_sync();
           uint32_t ro[32];
           tmem_ld_32x32b_x32(t_o, ro);
@@ -1237,10 +1245,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       }
       const float nm = -m_run;
       const float es = plain ? sl2 : 1.0f;
-      // P buffer sb was last read by P V of chunk g-2
-      if (g >= 2) mbar_wait_fast(bar_wg + BAR_O + (uint32_t)sb * 8u, (uint32_t)((g - 2) >> 1) & 1u);
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t p_dst = p_swz + (uint32_t)sb * SP3_BYTES;
 #pragma unroll
       for (int cc = 0; cc < CH3 / 8; ++cc) {
         const int j = cc * 8;
@@ -1254,7 +1259,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
-        sts128(p_dst ^ ((uint32_t)cc << 4),
+      }
+      // the P buffer (and O) are free once P V of the previous chunk has landed
+      if (g >= 1) mbar_wait_fast(bar_wg + BAR_O, (uint32_t)(g - 1) & 1u);
+#pragma unroll
+      for (int cc = 0; cc < CH3 / 8; ++cc) {
+        const int j = cc * 8;
+        sts128(p_swz ^ ((uint32_t)cc << 4),
                pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
                pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
       }
@@ -1268,7 +1279,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       }
       fence_proxy_async_smem();
       tc_fence_before_sync();
-      mbar_arrive_a(bar_wg + BAR_P + (uint32_t)sb * 8u);
+      mbar_arrive_a(bar_wg + BAR_P);
       if (++k == n_uch) {
         k = 0; l_fin = l_run; m_fin = m_run; ++P;
         if (++pj == passes_per_tile) { pj = 0; q_tile += T; }
@@ -1309,7 +1320,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           const float ms = (m_all == -INFINITY) ? 0.f : m_all;
           const float ws = split_keys ? fast_exp2(ml.x - ms) : 1.0f;
           if (split_keys) l_all = fmaf(ml.y, ws, l_all);
-          const uint32_t base = smem_u32(sP_all + ow * 2 * SP3_BYTES) + (uint32_t)wtid * 128u;
+          const uint32_t base = smem_u32(sP_all + ow * SP3_BYTES) + (uint32_t)wtid * 128u;
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             const float4 f = lds128f(base + (((uint32_t)ch ^ ((uint32_t)wtid & 7u)) << 4));
