@@ -50,7 +50,8 @@ constexpr int SA_GATHER = 6, SA_HALO = 4;       // A ring depth (all stages may 
 constexpr int kMaxDynSmem = 227 * 1024 - 12288;        // static smem (barriers, bias, LN exchange) counts too
 constexpr int MAX_STAGES = 8;
 
-enum { MODE_GATHER = 0, MODE_HALO = 1, MODE_LINEAR = 2 };
+enum { MODE_GATHER = 0, MODE_HALO = 1, MODE_LINEAR = 2, MODE_TAP = 3, MODE_PATCH = 4 };
+enum { A_SW128 = 0, A_SW64 = 1, A_NOSWZ = 2 };          // smem image of a TAP-mode A stage
 
 struct KArgs {
   CobevtConvParams p;
@@ -58,7 +59,10 @@ struct KArgs {
   int32_t mode, sa, sb, resident_b;
   int32_t tiles_y, tiles_x, nslab;      // HALO geometry
   int32_t cin_log2, kw_magic;           // GATHER tap decode without divisions (cin_log2 < 0: generic)
-  int32_t use_tma;                      // A operand through TMA tensor loads (HALO / LINEAR) instead of per-thread cp.async
+  int32_t use_tma;                      // A operand through TMA tensor loads (HALO / LINEAR / TAP) instead of per-thread cp.async
+  int32_t tap_c, taps_per_kb, slabs_per_tap, a_layout;   // TAP: channels per tensor load, taps per 64-wide K block, ...
+  int32_t patch_w, patch_h;             // PATCH: input patch (pixels) of one 16 x 8 output tile
+  int32_t ntaps, tap_kw;                // TAP: tensor loads per tile and taps per filter row (1 when a row's taps are fused)
   int32_t dbg;                          // COBEVT_CONV_DEBUG bits (profiling experiments only): 1 no epilogue I/O, 2 no A loads, 4 no MMA
   uint32_t idesc;
   alignas(64) CUtensorMap tmap;         // HALO: {C, W, H, N} box {64, 10, 18, 1}; LINEAR: {K, M} box {64, 128}; SWIZZLE_128B
@@ -117,7 +121,7 @@ __device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32
 // output row (TMEM lane) -> linear output pixel index, or -1
 __device__ __forceinline__ int64_t out_row_index(const KArgs& a, int m_tile, int row) {
   const CobevtConvParams& p = a.p;
-  if (a.mode == MODE_HALO) {
+  if (a.mode == MODE_HALO || a.mode == MODE_TAP || a.mode == MODE_PATCH) {
     const int per_img = a.tiles_y * a.tiles_x;
     const int n = m_tile / per_img;
     const int t = m_tile - n * per_img;
@@ -538,6 +542,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
               if (!a.resident_b)
                 for (int tap = 0; tap < 9; ++tap) load_b(wb, tap * a.nslab + slab);
             }
+          } else if (a.mode == MODE_PATCH) {
+            // 8-channel input (one pixel = 16 bytes = one core-matrix row): the raw input patch of the tile is
+            // loaded once, unswizzled; the MMA descriptors walk it in place (see the issuer)
+            const int n = m_tile / per_img;
+            const int t = m_tile - n * per_img;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            mbar_wait(&a_empty[ps], pph);
+            mbar_arrive_expect_tx(&a_full[ps], (uint32_t)(a.patch_w * a.patch_h * 16));
+            tma_load_4d(sA + ps * A_GATHER_BYTES, &a.tmap, &a_full[ps], 0, tx * TILE_W * p.stride_w - p.pad_w,
+                        ty * TILE_H * p.stride_h - p.pad_h, n);
+            if (++ps == SA) { ps = 0; pph ^= 1u; }
+          } else if (a.mode == MODE_TAP) {
+            // general strided conv: one strided 16 x 8 pixel box per filter tap (and 64-channel slab); the
+            // taps of a K block sit side by side in the stage (whole 128-byte rows, 64-byte rows or 16-byte
+            // core-matrix columns, see a_layout).  Padding = out-of-bounds zero fill.
+            const int n = m_tile / per_img;
+            const int t = m_tile - n * per_img;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            const int x0 = tx * TILE_W * p.stride_w - p.pad_w, y0 = ty * TILE_H * p.stride_h - p.pad_h;
+            const int ntaps = a.ntaps;
+            const uint32_t tap_bytes = (uint32_t)BLOCK_M * a.tap_c * 2;
+            int tap = 0, slab = 0, ky = 0, kx = 0;
+            for (int kb = 0; kb < KB; ++kb) {
+              mbar_wait(&a_empty[ps], pph);
+              uint8_t* dst = sA + ps * A_GATHER_BYTES;
+              const int nload = a.slabs_per_tap > 1 ? 1 : (ntaps - tap < a.taps_per_kb ? ntaps - tap : a.taps_per_kb);
+              mbar_arrive_expect_tx(&a_full[ps], nload * tap_bytes);
+              for (int j = 0; j < nload; ++j) {
+                tma_load_4d(dst + j * tap_bytes, &a.tmap, &a_full[ps], slab * 64, x0 + kx, y0 + ky, n);
+                if (++slab == a.slabs_per_tap) { slab = 0; ++tap; if (++kx == a.tap_kw) { kx = 0; ++ky; } }
+              }
+              if (++ps == SA) { ps = 0; pph ^= 1u; }
+              if (!a.resident_b) load_b(wb, kb);
+            }
           } else {
             for (int kb = 0; kb < KB; ++kb) {
               mbar_wait(&a_empty[ps], pph);
@@ -576,6 +614,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const uint64_t tA_h = make_smem_desc(0, 16, HALO_W * 128, LAYOUT_SW128);
       const uint32_t lo0 = (uint32_t)tA_g;                 // LBO bits only (same for all three)
       const uint32_t hiA_g = (uint32_t)(tA_g >> 32), hiA_h = (uint32_t)(tA_h >> 32), hiB = hiA_g;
+      const uint64_t tA_64 = make_smem_desc(0, 16, 512, LAYOUT_SW64);
+      const uint64_t tA_n = make_smem_desc(0, 2048, 128, LAYOUT_NONE);
+      const uint32_t hiA_64 = (uint32_t)(tA_64 >> 32), hiA_n = (uint32_t)(tA_n >> 32), lo_n = (uint32_t)tA_n;
       const uint32_t idesc = a.idesc;
       const bool do_mma = !(a.dbg & 4);
       if (a.resident_b) mbar_wait(&b_res_full, 0);
@@ -585,7 +626,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + buf * BN;
         uint32_t accum = 0;
-        if (a.mode != MODE_HALO) {
+        if (a.mode == MODE_PATCH) {
+          // A row m = output pixel (y, x) of the 16 x 8 tile; its K slice for filter row ky is the KW*8 contiguous
+          // elements starting at input pixel (y*sh + ky, x).  In the unswizzled patch, pixels are 16 bytes apart, so
+          // the 8 x 16 B core matrix of K chunk kx is 8 consecutive pixels starting at x + kx: overlapping core
+          // matrices, LBO = 16 B between K chunks, SBO = sh patch rows between 8-row groups.  No im2col copy exists.
+          mbar_wait(&a_full[sa_], aph);
+          tc_fence_after_sync();
+          const uint32_t pitch = (uint32_t)a.patch_w * 16u;
+          const uint64_t tA_p = make_smem_desc(0, 16, (uint32_t)p.stride_h * pitch, LAYOUT_NONE);
+          const uint32_t lo_p = (uint32_t)tA_p, hi_p = (uint32_t)(tA_p >> 32);
+          const uint32_t a_addr = smem_u32(sA + sa_ * A_GATHER_BYTES);
+          const uint32_t b_base = lo0 | (smem_u32(sB) >> 4);
+          if (elect_one()) {
+            if (do_mma) {
+              int j = 0;
+              for (int ky = 0; ky < p.KH; ++ky)
+                for (int kp = 0; kp < p.KW / 2; ++kp, ++j)
+                  umma_lohi(d_tmem, lo_p | ((a_addr + ky * pitch + kp * 32) >> 4), hi_p,
+                            b_base + (j >> 2) * (kBStage >> 4) + (j & 3) * 2, hiB, idesc, j ? 1u : 0u);
+            }
+            umma_commit(&a_empty[sa_]);
+          }
+          if (++sa_ == SA) { sa_ = 0; aph ^= 1u; }
+        } else if (a.mode != MODE_HALO) {
           for (int kb = 0; kb < KB; ++kb) {
             mbar_wait(&a_full[sa_], aph);
             if (!a.use_tma) fence_proxy_async_smem();     // cp.async (generic proxy) bytes -> visible to the UMMA (async proxy)
@@ -597,12 +661,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
               sb_addr = smem_u32(sB + sb_ * kBStage);
             }
             tc_fence_after_sync();
-            const uint32_t a_lo = lo0 | (smem_u32(sA + sa_ * A_GATHER_BYTES) >> 4);
+            const uint32_t a_addr = smem_u32(sA + sa_ * A_GATHER_BYTES) >> 4;
+            const uint32_t a_lo = lo0 | a_addr;
             const uint32_t b_lo = lo0 | (sb_addr >> 4);
             if (elect_one()) {
               if (do_mma) {
+                if (a.a_layout == A_SW128) {
 #pragma unroll
-                for (int ks = 0; ks < BLOCK_K / 16; ++ks) umma_lohi(d_tmem, a_lo + ks * 2, hiA_g, b_lo + ks * 2, hiB, idesc, (accum | ks) ? 1u : 0u);
+                  for (int ks = 0; ks < BLOCK_K / 16; ++ks) umma_lohi(d_tmem, a_lo + ks * 2, hiA_g, b_lo + ks * 2, hiB, idesc, (accum | ks) ? 1u : 0u);
+                } else {
+                  // TAP stages of narrow inputs: 32 channels -> two SWIZZLE_64B tiles (one per tap, 8 KB);
+                  // 8 channels -> eight 2 KB columns of 8 x 16 B core matrices (no swizzle, LBO = next tap)
+                  const int rem = a.K - kb * BLOCK_K;
+                  const int nks = rem >= BLOCK_K ? BLOCK_K / 16 : (rem + 15) / 16;
+                  for (int ks = 0; ks < nks; ++ks) {
+                    const uint32_t alo = a.a_layout == A_SW64 ? (lo0 | (a_addr + (ks >> 1) * 512 + (ks & 1) * 2))
+                                                               : (lo_n | (a_addr + ks * 256));
+                    umma_lohi(d_tmem, alo, a.a_layout == A_SW64 ? hiA_64 : hiA_n, b_lo + ks * 2, hiB, idesc, (accum | ks) ? 1u : 0u);
+                  }
+                }
               }
               umma_commit(&a_empty[sa_]);
               if (!a.resident_b) umma_commit(&b_empty[sb_]);
@@ -685,6 +762,25 @@ bool make_a_tmap(KArgs& a) {
     const cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (a.mode == MODE_PATCH) {
+    const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Win * p.Cin * 2, (cuuint64_t)p.Hin * p.Win * p.Cin * 2};
+    const cuuint32_t box[4] = {8, (cuuint32_t)a.patch_w, (cuuint32_t)a.patch_h, 1};
+    const cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else if (a.mode == MODE_TAP) {
+    // (fused filter rows: the KW taps of one row are KW*Cin contiguous elements starting at the pixel, i.e. a
+    //  tensor of overlapping windows -- pixel stride Cin elements, window length tap_c -- is loaded instead)
+    const bool fused_row = a.tap_kw == 1 && p.KW > 1;
+    const cuuint64_t dims[4] = {(cuuint64_t)(fused_row ? a.tap_c : p.Cin), (cuuint64_t)(fused_row ? p.Win - p.KW + 1 : p.Win), (cuuint64_t)p.Hin, (cuuint64_t)p.N};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Win * p.Cin * 2, (cuuint64_t)p.Hin * p.Win * p.Cin * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)a.tap_c, (cuuint32_t)((TILE_W - 1) * p.stride_w + 1), (cuuint32_t)((TILE_H - 1) * p.stride_h + 1), 1};
+    const cuuint32_t es[4] = {1, (cuuint32_t)p.stride_w, (cuuint32_t)p.stride_h, 1};
+    const CUtensorMapSwizzle sw = a.a_layout == A_SW128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                  : a.a_layout == A_SW64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else {
     const cuuint64_t dims[2] = {(cuuint64_t)p.Cin, (cuuint64_t)a.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.Cin * 2};
@@ -716,6 +812,7 @@ int launch(KArgs& a, cudaStream_t st) {
     a.sb = sb;
     smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
   }
+  if (a.mode == MODE_PATCH && !a.resident_b) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: PATCH mode needs the resident weight image");
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
@@ -811,14 +908,50 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
       a.kw_magic = (65536 + p->KW - 1) / p->KW;
     }
   }
-  a.total_tiles = a.m_tiles * a.n_tiles;
   {
-    static int no_tma = -1;
+    static int no_tma = -1, no_tap = -1;
     if (no_tma < 0) { const char* e = getenv("COBEVT_CONV_NOTMA"); no_tma = e ? atoi(e) : 0; }
+    if (no_tap < 0) { const char* e = getenv("COBEVT_CONV_NOTAP"); no_tap = e ? atoi(e) : 0; }   // 1 no TAP, 2 no PATCH, 4 no fused rows, 8 only Cin>=64 TAP
     a.use_tma = 0;
-    if (!no_tma && (a.mode == MODE_HALO || a.mode == MODE_LINEAR) && (reinterpret_cast<uintptr_t>(p->x) & 15) == 0)
+    const bool aligned = (reinterpret_cast<uintptr_t>(p->x) & 15) == 0;
+    if (!no_tma && aligned && (a.mode == MODE_HALO || a.mode == MODE_LINEAR)) {
       a.use_tma = make_a_tmap(a) ? 1 : 0;
+    } else if (!no_tma && aligned && a.mode == MODE_GATHER && !p->in_upsample &&
+               (p->Cin == 8 || p->Cin == 32 || p->Cin % 64 == 0) && p->stride_h <= 8 && p->stride_w <= 8 && !(no_tap & 1) &&
+               !((no_tap & 8) && p->Cin < 64)) {
+      // strided / narrow convolutions: per-tap strided tensor loads over 16 x 8 output-pixel tiles
+      KArgs t = a;
+      t.mode = MODE_TAP;
+      t.tiles_y = cobevt::ceil_div(p->OH, TILE_H);
+      t.tiles_x = cobevt::ceil_div(p->OW, TILE_W);
+      t.m_tiles = p->N * t.tiles_y * t.tiles_x;
+      t.tap_c = p->Cin < 64 ? p->Cin : 64;
+      t.taps_per_kb = p->Cin < 64 ? 64 / p->Cin : 1;
+      t.slabs_per_tap = p->Cin < 64 ? 1 : p->Cin / 64;
+      t.a_layout = p->Cin == 8 ? A_NOSWZ : (p->Cin == 32 ? A_SW64 : A_SW128);
+      t.ntaps = p->KH * p->KW;
+      t.tap_kw = p->KW;
+      if (!(no_tap & 4) && p->stride_w == 1 && p->pad_w == 0 && p->KW > 1 && p->Cin < 64 && (p->Cin * p->KW == 32 || p->Cin * p->KW == 64)) {
+        t.tap_c = p->Cin * p->KW;           // one load per filter row
+        t.taps_per_kb = 64 / t.tap_c;
+        t.a_layout = t.tap_c == 32 ? A_SW64 : A_SW128;
+        t.ntaps = p->KH;
+        t.tap_kw = 1;
+      }
+      // 8-channel inputs with unit stride along W: the raw input patch of a tile is the A operand (PATCH mode),
+      // provided the whole packed weight can stay resident
+      const int pw = TILE_W + p->KW - 1, ph = (TILE_H - 1) * p->stride_h + p->KH;
+      if (!(no_tap & 2) && p->Cin == 8 && p->stride_w == 1 && p->KW % 2 == 0 && pw <= 256 && ph <= 256 && pw * ph * 16 <= A_GATHER_BYTES &&
+          a.n_tiles == 1 && (int64_t)a.KB * p->block_n * BLOCK_K * 2 <= 96 * 1024) {
+        t.mode = MODE_PATCH;
+        t.patch_w = pw;
+        t.patch_h = ph;
+        t.a_layout = A_SW128;
+      }
+      if (make_a_tmap(t)) { a = t; a.use_tma = 1; }
+    }
   }
+  a.total_tiles = a.m_tiles * a.n_tiles;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->block_n) {

@@ -91,6 +91,31 @@ def test_conv_upsampled_input():
     assert relerr(y, ref) < 2e-3
 
 
+
+@pytest.mark.parametrize("cfg", [
+    # N, H, W, Cin, Cout, (kh, kw), (sh, sw), (ph, pw)   -- the per-tap / patch TMA producer modes
+    (2, 40, 48, 64, 128, (3, 3), (2, 2), (1, 1)),
+    (2, 40, 48, 128, 256, (3, 3), (2, 2), (1, 1)),      # two 64-channel slabs per tap
+    (2, 40, 48, 128, 256, (1, 1), (2, 2), (0, 0)),
+    (2, 40, 48, 64, 128, (6, 3), (2, 1), (2, 1)),       # PixelUnshuffle-folded downsample conv
+    (2, 37, 50, 8, 64, (7, 4), (2, 1), (0, 0)),         # stem on RGBx super-pixels: in-place im2col (PATCH)
+    (2, 30, 30, 8, 64, (7, 8), (2, 2), (3, 3)),         # 8 channels, strided along W: per-tap core-matrix columns
+    (2, 40, 48, 32, 32, (3, 3), (1, 1), (1, 1)),        # 32 channels: SWIZZLE_64B tap tiles
+])
+def test_conv_strided_tap_modes(cfg):
+    from cobevt_b200 import ops
+    N, H, W, Cin, Cout, (kh, kw), st, pd = cfg
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, H, W, Cin, generator=g).half().cuda()
+    w = torch.randn(Cout, Cin, kh, kw, generator=g) / math.sqrt(Cin * kh * kw)
+    b = torch.randn(Cout, generator=g)
+    pc = ops.PackedConv(w, b, "cuda")
+    y, _, _ = ops.conv2d_nhwc(x, pc, stride=st, pad=pd, act=0)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.half().float().cuda(), b.cuda(),
+                                     stride=st, padding=pd).permute(0, 2, 3, 1)
+    assert y.shape == ref.shape
+    assert relerr(y, ref) < 2e-3, relerr(y, ref)
+
 # ----------------------------------------------------------------------------- attention
 def partition(t, w1, w2, grid):
     """(B, n, H, W, C) -> (B, windows, n*w1*w2, C) with the reference's einops patterns."""

@@ -233,10 +233,69 @@ static int run_case(const char* name, uint32_t M, uint32_t N, uint32_t K, bool b
   return maxerr < 1e-3;
 }
 
+
+// A = im2col view of an unswizzled 8-channel input patch read IN PLACE: core matrices overlap (LBO = 16 B),
+// 8-row groups are `sh` patch rows apart.  B no-swizzle as in case 4.
+static int run_patch_case(const char* name, uint32_t pw, uint32_t ph, uint32_t sh, uint32_t KW, uint32_t ky0) {
+  const uint32_t M = 128, N = 64, K = KW * 8;
+  std::vector<float> P(ph * pw * 8), B(N * K);
+  srand(77);
+  for (auto& v : P) v = (float)((rand() % 17) - 8) / 8.0f;
+  for (auto& v : B) v = (float)((rand() % 13) - 6) / 4.0f;
+  const uint32_t a_bytes = ph * pw * 16, b_bytes = N * K * 2;
+  std::vector<uint8_t> ai(a_bytes, 0), bi(b_bytes, 0);
+  for (uint32_t i = 0; i < ph * pw * 8; ++i) { uint16_t u = f2h(P[i]); memcpy(&ai[i * 2], &u, 2); }
+  for (uint32_t n = 0; n < N; ++n)
+    for (uint32_t k = 0; k < K; ++k) { uint16_t u = f2h(B[n * K + k]); memcpy(&bi[(k / 8) * (N * 16) + n * 16 + (k % 8) * 2], &u, 2); }
+  std::vector<float> ref(M * N, 0.f);
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      float s = 0;
+      const uint32_t y = m / 8, x = m % 8;
+      for (uint32_t k = 0; k < K; ++k) s += h2f(f2h(P[((y * sh + ky0) * pw + x + k / 8) * 8 + k % 8])) * h2f(f2h(B[n * K + k]));
+      ref[m * N + n] = s;
+    }
+  ProbeArgs a{};
+  a.a_layout = LAYOUT_NONE; a.a_lbo = 16; a.a_sbo = sh * pw * 16;
+  a.b_layout = LAYOUT_NONE; a.b_lbo = N * 16; a.b_sbo = 128;
+  a.idesc = make_idesc_f16(M, N, false, false, false);
+  for (uint32_t ks = 0; ks < K / 16; ++ks) { a.a_koff[ks] = ky0 * pw * 16 + ks * 32; a.b_koff[ks] = ks * 2 * N * 16; }
+  uint8_t *da, *db; float* dd;
+  cudaMalloc(&da, a_bytes); cudaMalloc(&db, b_bytes); cudaMalloc(&dd, M * N * 4);
+  cudaMemcpy(da, ai.data(), a_bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(db, bi.data(), b_bytes, cudaMemcpyHostToDevice);
+  cudaMemset(dd, 0xFF, M * N * 4);
+  a.a_bytes = a_bytes; a.b_bytes = b_bytes; a.n = N; a.nk = K / 16;
+  uint32_t smem = ((a_bytes + 1023u) & ~1023u) + b_bytes + 1024;
+  cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  probe_kernel<<<1, 128, smem>>>(da, db, dd, a);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("%-44s CUDA ERROR %s\n", name, cudaGetErrorString(e)); exit(3); }
+  std::vector<float> out(M * N);
+  cudaMemcpy(out.data(), dd, M * N * 4, cudaMemcpyDeviceToHost);
+  double maxerr = 0; int bad_rows = 0;
+  for (uint32_t m = 0; m < M; ++m) {
+    double em = 0;
+    for (uint32_t n = 0; n < N; ++n) { double d = fabs((double)out[m * N + n] - ref[m * N + n]); if (!(d == d)) d = 1e30; if (d > em) em = d; }
+    if (em > 1e-3) ++bad_rows;
+    if (em > maxerr) maxerr = em;
+  }
+  printf("%-44s maxerr %.4g  bad rows %d  %s\n", name, maxerr, bad_rows, maxerr < 1e-3 ? "PASS" : "FAIL");
+  cudaFree(da); cudaFree(db); cudaFree(dd);
+  return maxerr < 1e-3;
+}
+
 int main(int argc, char** argv) {
   int only = argc > 1 ? atoi(argv[1]) : -1;
   int id = 0;
   auto want = [&](int i) { return only < 0 || only == i; };
+  if (only == 100) {
+    run_patch_case("patch pw=11 sh=2 ky=0", 11, 37, 2, 4, 0);
+    run_patch_case("patch pw=11 sh=2 ky=3", 11, 37, 2, 4, 3);
+    run_patch_case("patch pw=8 sh=1 ky=0 (cores 128B-aligned)", 8, 16, 1, 2, 0);
+    run_patch_case("patch pw=16 sh=1 ky=1", 16, 18, 1, 4, 1);
+    return 0;
+  }
   if (only < 0) run_micro();
 
   // ---- case 0/1: SW128 K-major A and B, K = 128 (two 64-wide k-blocks) -------------
