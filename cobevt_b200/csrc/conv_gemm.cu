@@ -49,6 +49,7 @@ constexpr int REGS_WORKERS = 104, REGS_CONTROL = 40;   // setmaxnreg split: 16 w
 constexpr int SA_GATHER = 6, SA_HALO = 4;       // A ring depth (all stages may be in flight)
 constexpr int kMaxDynSmem = 227 * 1024 - 12288;        // static smem (barriers, bias, LN exchange) counts too
 constexpr int MAX_STAGES = 8;
+constexpr int STG_WARP_BYTES = 4096;                   // TMA-store staging per epilogue warp: 32 rows x <= 128 B
 
 enum { MODE_GATHER = 0, MODE_HALO = 1, MODE_LINEAR = 2, MODE_TAP = 3, MODE_PATCH = 4 };
 enum { A_SW128 = 0, A_SW64 = 1, A_NOSWZ = 2 };          // smem image of a TAP-mode A stage
@@ -65,6 +66,8 @@ struct KArgs {
   int32_t ntaps, tap_kw;                // TAP: tensor loads per tile and taps per filter row (1 when a row's taps are fused)
   int32_t dbg;                          // COBEVT_CONV_DEBUG bits (profiling experiments only): 1 no epilogue I/O, 2 no A loads, 4 no MMA
   uint32_t idesc;
+  int32_t st_tma;                       // 16-bit outputs leave through per-warp smem tiles + TMA tensor stores
+  alignas(64) CUtensorMap tmY, tmYln;   // output maps: {Cout, M} box {U, 32}  or  {Cout, OW, OH, N} box {U, 8, 4, 1}
   alignas(64) CUtensorMap tmap;         // HALO: {C, W, H, N} box {64, 10, 18, 1}; LINEAR: {K, M} box {64, 128}; SWIZZLE_128B
 };
 
@@ -164,6 +167,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   const int a_stage_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
   uint8_t* sA = smem;
   uint8_t* sB = smem + SA * a_stage_bytes;
+  uint8_t* sStage = sB + (a.resident_b ? a.KB * kBStage : SB * kBStage);   // 16 x STG_WARP_BYTES when a.st_tma
   __shared__ uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES];
   __shared__ uint64_t acc_full[4], acc_empty[4], b_res_full;
   __shared__ uint32_t tmem_base_s;
@@ -366,6 +370,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const bool row_ok = m >= 0;
       const int64_t mr = p.res_rows > 0 ? (int64_t)((uint32_t)(row_ok ? m : 0) % (uint32_t)p.res_rows) : m;
       const uint32_t trow = tmem_base + ((uint32_t)(q4 * 32) << 16) + buf * BN + hf * CW;
+      // TMA-store path: the warp's 32 x U tile is written to its staging buffer in the output map's swizzle
+      // (inner box = U * 2 bytes: SWIZZLE_128B / 64B / 32B) and leaves as one tensor store (full lines, clipped
+      // at the tensor bounds, no store instructions or address arithmetic in this warp).
+      const uint32_t stg = smem_u32(sStage) + (uint32_t)(team * 8 + e) * STG_WARP_BYTES;
+      const bool st_tma = a.st_tma && !(a.dbg & 1);
+      auto tma_out = [&](const CUtensorMap* tm, int n0c, bool relu, const float (&vv)[U]) {
+        constexpr int CH16 = U / 8;                     // 16-byte pieces per row
+        constexpr int RPL = 128 / (U * 2);              // rows per 128-byte line
+        if (lane == 0) bulk_wait_read0();               // the previous store has finished reading the buffer
+        __syncwarp();
+#pragma unroll
+        for (int ck = 0; ck < CH16; ++ck) {
+          uint32_t w0 = pack2(vv[ck * 8 + 0], vv[ck * 8 + 1], bf16), w1 = pack2(vv[ck * 8 + 2], vv[ck * 8 + 3], bf16);
+          uint32_t w2 = pack2(vv[ck * 8 + 4], vv[ck * 8 + 5], bf16), w3 = pack2(vv[ck * 8 + 6], vv[ck * 8 + 7], bf16);
+          if (relu) { w0 = relu2(w0, bf16); w1 = relu2(w1, bf16); w2 = relu2(w2, bf16); w3 = relu2(w3, bf16); }
+          sts128(stg + (uint32_t)(lane * (U * 2)) + ((((uint32_t)ck ^ ((uint32_t)(lane / RPL) & (CH16 - 1)))) << 4), w0, w1, w2, w3);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (a.mode == MODE_LINEAR || a.mode == MODE_GATHER) {
+            tma_store_2d(tm, stg, n0c, m_tile * BLOCK_M + q4 * 32);
+          } else {
+            const int per_img = a.tiles_y * a.tiles_x;
+            const int n = m_tile / per_img;
+            const int t = m_tile - n * per_img;
+            const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
+            tma_store_4d(tm, stg, n0c, tx * TILE_W, ty * TILE_H + q4 * 4, n);
+          }
+          bulk_commit();
+        }
+      };
 #pragma unroll 1
       for (int u = 0; u < NU; ++u) {
         const int col = hf * CW + u * U;           // column inside the tile
@@ -432,6 +468,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < U; ++j) v[j] = gelu_erf(v[j]);
         }
+        if (st_tma && p.y) {
+          tma_out(&a.tmY, n0, relu_packed, v);
+        } else
         if (live && p.y) {
           uint8_t* yp = reinterpret_cast<uint8_t*>(p.y) + (m * p.Cout + n0) * 2;
 #pragma unroll
@@ -486,7 +525,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
               var = (m2 + o.y + dlt * dlt * (float)(U / 2)) * (1.0f / (2 * U));
             }
             const float rstd = rsqrtf(var + p.ln_eps);
-            if (live) {
+            if (st_tma) {
+#pragma unroll
+              for (int j = 0; j < U; ++j) v[j] = fmaf((v[j] - mean) * rstd, sGamma[(col + j) & 127], sBeta[(col + j) & 127]);
+              tma_out(&a.tmYln, n0, false, v);
+            } else if (live) {
               uint8_t* yp = reinterpret_cast<uint8_t*>(p.y_ln) + (m * p.Cout + n0) * 2;
 #pragma unroll
               for (int j = 0; j < U; ++j) v[j] = fmaf((v[j] - mean) * rstd, sGamma[(col + j) & 127], sBeta[(col + j) & 127]);
@@ -504,6 +547,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         }
       }
     }
+    if (a.st_tma && lane == 0) bulk_wait0();      // every tensor store of this warp has completed
   } else if (warp == 16) {
     // ================================ loader ==============================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CONTROL));
@@ -792,26 +836,78 @@ bool make_a_tmap(KArgs& a) {
   return r == CUDA_SUCCESS;
 }
 
+
+// output tensor maps for the TMA-store epilogue; U = columns per epilogue unit of this BN
+bool make_out_tmaps(KArgs& a, int U) {
+  cobevt::EncodeTiledFn enc = cobevt::get_encode_tiled();
+  if (!enc) return false;
+  const CobevtConvParams& p = a.p;
+  const CUtensorMapDataType dt = p.dtype == COBEVT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  const CUtensorMapSwizzle sw = U == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (U == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  auto one = [&](CUtensorMap* tm, void* base) -> bool {
+    if (!base) return true;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    CUresult r;
+    if (a.mode == MODE_LINEAR || a.mode == MODE_GATHER) {
+      const cuuint64_t dims[2] = {(cuuint64_t)p.Cout, (cuuint64_t)a.M};
+      const cuuint64_t strides[1] = {(cuuint64_t)p.Cout * 2};
+      const cuuint32_t box[2] = {(cuuint32_t)U, 32};
+      const cuuint32_t es[2] = {1, 1};
+      r = enc(tm, dt, 2, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      const cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.OW, (cuuint64_t)p.OH, (cuuint64_t)p.N};
+      const cuuint64_t strides[3] = {(cuuint64_t)p.Cout * 2, (cuuint64_t)p.OW * p.Cout * 2, (cuuint64_t)p.OH * p.OW * p.Cout * 2};
+      const cuuint32_t box[4] = {(cuuint32_t)U, TILE_W, 4, 1};
+      const cuuint32_t es[4] = {1, 1, 1, 1};
+      r = enc(tm, dt, 4, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    return r == CUDA_SUCCESS;
+  };
+  return one(&a.tmY, p.y) && one(&a.tmYln, p.y_ln);
+}
+
 template <int BN>
 int launch(KArgs& a, cudaStream_t st) {
   constexpr int kBStage = BN * BLOCK_K * 2;
+  constexpr int CWh = BN >= 64 ? BN / 2 : BN;            // mirrors the epilogue's CW / U
+  constexpr int Uh = CWh > 64 ? 64 : CWh;
   const int a_bytes = a.mode == MODE_HALO ? A_HALO_BYTES : A_GATHER_BYTES;
-  const int budget = kMaxDynSmem - 1024;
-  a.sa = a.mode == MODE_HALO ? SA_HALO : SA_GATHER;
-  const int64_t b_all = (int64_t)a.KB * kBStage;
-  a.resident_b = (a.n_tiles == 1 && b_all <= budget - a.sa * a_bytes && b_all < (1 << 20)) ? 1 : 0;
-  int64_t smem;
-  if (a.resident_b) {
-    a.sb = 1;
-    smem = 1024 + (int64_t)a.sa * a_bytes + b_all;
-  } else {
-    int sb = (budget - a.sa * a_bytes) / kBStage;
-    if (sb > MAX_STAGES) sb = MAX_STAGES;
-    if (sb < 2) { a.sa = 2; sb = (budget - a.sa * a_bytes) / kBStage; }
-    if (sb < 2) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: no smem for the B ring (BN=%d)", BN);
-    a.sb = sb;
-    smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
+  static int no_tst = -1;
+  if (no_tst < 0) { const char* e = getenv("COBEVT_CONV_NOTMASTORE"); no_tst = e ? atoi(e) : 0; }
+  // 16-bit outputs through TMA tensor stores when the staging tiles (16 warps x 4 KB) fit next to the rings
+  const bool want_st = !no_tst && a.use_tma && (a.p.y || a.p.y_ln) && a.p.Cout % 8 == 0 && Uh >= 16;
+  const int sa_full = a.mode == MODE_HALO ? SA_HALO : SA_GATHER;
+  const int cand_st[3] = {1, 1, 0};
+  const int cand_sa[3] = {sa_full, a.mode == MODE_HALO ? 3 : 4, sa_full};
+  int64_t smem = 0;
+  bool fit = false;
+  for (int c = want_st ? 0 : 2; c < 3 && !fit; ++c) {
+    a.st_tma = cand_st[c];
+    a.sa = cand_sa[c];
+    const int budget = kMaxDynSmem - 1024 - (a.st_tma ? 16 * STG_WARP_BYTES : 0);
+    const int64_t b_all = (int64_t)a.KB * kBStage;
+    a.resident_b = (a.n_tiles == 1 && b_all <= budget - a.sa * a_bytes && b_all < (1 << 20)) ? 1 : 0;
+    if (a.resident_b) {
+      a.sb = 1;
+      smem = 1024 + (int64_t)a.sa * a_bytes + b_all;
+      fit = true;
+    } else {
+      int sb = (budget - a.sa * a_bytes) / kBStage;
+      if (sb > MAX_STAGES) sb = MAX_STAGES;
+      if (sb < 3 && a.st_tma) continue;                      // the weight ring matters more than the store path
+      if (sb < 2) { a.sa = 2; sb = (budget - a.sa * a_bytes) / kBStage; }
+      if (sb < 2) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: no smem for the B ring (BN=%d)", BN);
+      a.sb = sb;
+      smem = 1024 + (int64_t)a.sa * a_bytes + (int64_t)sb * kBStage;
+      fit = true;
+    }
   }
+  if (a.st_tma && !make_out_tmaps(a, Uh)) {                 // no tensor maps: direct stores (the staging area stays unused)
+    a.st_tma = 0;
+  }
+  if (a.st_tma) smem += 16 * STG_WARP_BYTES;
   if (a.mode == MODE_PATCH && !a.resident_b) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: PATCH mode needs the resident weight image");
   static bool attr_set = false;
   if (!attr_set) {

@@ -233,6 +233,21 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
 }
 
 
+// TMA tensor stores (tile mode): the shared-memory box (in the tensor map's swizzle) is written to global
+// memory, clipped at the tensor bounds.  Bulk-group completion: commit, then wait_group(.read) before the
+// staging buffer is reused / the CTA exits.
+__device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------
 // Bulk async copy global -> shared (TMA engine, no tensor map): completes
 // `bytes` on the mbarrier.  Size and both addresses are multiples of 16.

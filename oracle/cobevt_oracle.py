@@ -399,7 +399,7 @@ def warp_affine_pixels(src, T, mode):
     with align_corners=True the normalise / affine_grid / grid_sample chain samples
     src at T^-1 (x_dst, y_dst, 1), zeros outside.  src (N, C, H, W), T (N, 3, 3)."""
     N, C, H, W = src.shape
-    Ti = T.inverse()
+    Ti = T.float().inverse().to(T.dtype)   # (fp32 solve: linalg.inv has no half kernel; only the eager-autocast proxy ever gets here in 16 bit)
     dev = src.device
     ys, xs = torch.meshgrid(torch.arange(H, dtype=torch.float32, device=dev), torch.arange(W, dtype=torch.float32, device=dev), indexing="ij")
     p = torch.stack([xs.reshape(-1), ys.reshape(-1), torch.ones(H * W, device=dev)], 0)       # 3, HW
