@@ -877,7 +877,9 @@ int launch(KArgs& a, cudaStream_t st) {
   static int no_tst = -1;
   if (no_tst < 0) { const char* e = getenv("COBEVT_CONV_NOTMASTORE"); no_tst = e ? atoi(e) : 0; }
   // 16-bit outputs through TMA tensor stores when the staging tiles (16 warps x 4 KB) fit next to the rings
-  const bool want_st = !no_tst && a.use_tma && (a.p.y || a.p.y_ln) && a.p.Cout % 8 == 0 && Uh >= 16;
+  // (token GEMMs only: they are store-bound; for the 3x3 convs the staging area costs ring depth and the narrow
+  //  per-pixel boxes are no better than direct stores -- measured, profiles/r01i_launch_detail.log)
+  const bool want_st = !no_tst && a.use_tma && a.mode == MODE_LINEAR && (a.p.y || a.p.y_ln) && a.p.Cout % 8 == 0 && Uh == 64;
   const int sa_full = a.mode == MODE_HALO ? SA_HALO : SA_GATHER;
   const int cand_st[3] = {1, 1, 0};
   const int cand_sa[3] = {sa_full, a.mode == MODE_HALO ? 3 : 4, sa_full};
