@@ -42,6 +42,8 @@ class AttnParams(ctypes.Structure):
         ("qmap", TokenMap), ("kvmap", TokenMap),
         ("B", c_i32), ("heads", c_i32),
         ("q_stride", c_i32), ("kv_stride", c_i32), ("out_stride", c_i32), ("q_mean", c_i32), ("scale", c_f32), ("dtype", c_i32),
+        ("part", c_vp), ("kv_view0", c_i32), ("kv_views_total", c_i32), ("kv_segments", c_i32),
+        ("part_segment_stride", ctypes.c_int64),
     ]
 
 
@@ -67,6 +69,9 @@ def lib():
         L.cobevt_conv2d_nhwc_fwd.argtypes = [ctypes.POINTER(ConvParams), c_vp]
         L.cobevt_window_attn_fwd.restype = ctypes.c_int
         L.cobevt_window_attn_fwd.argtypes = [ctypes.POINTER(AttnParams), c_vp]
+        L.cobevt_attn_merge.restype = ctypes.c_int
+        L.cobevt_attn_merge.argtypes = [c_vp, c_i32, ctypes.c_int64, c_vp, ctypes.POINTER(TokenMap), c_i32, c_i32, c_i32,
+                                        c_i32, c_i32, c_vp]
         for name, argt in _ELTWISE_SIGS.items():
             fn = getattr(L, name)
             fn.restype = ctypes.c_int
@@ -102,5 +107,5 @@ def check(rc, what):
 
 EXPORTED_SYMBOLS = [
     "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
-    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd",
+    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge",
 ] + list(_ELTWISE_SIGS)

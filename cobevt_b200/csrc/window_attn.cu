@@ -39,6 +39,7 @@ struct AArgs {
   int32_t dbg;   // COBEVT_ATTN_DEBUG (timing experiments only; results are wrong): 1 no MUFU, 2 no P stores, 4 no proxy fence, 8 second warpgroup idle
   int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
   uint32_t idesc_qk, idesc_pv;
+  int32_t kv_vt, kv_segs;             // views of the K/V tensors (batch stride in views); key segments per launch
   int32_t kv_tma;                     // resident K / V windows are fetched by two 4-D TMA tensor loads
   alignas(64) CUtensorMap tmK, tmV;   // {C, Wv, Hv, B*views}, box {32, w2 (span), w1 (span), views}, SWIZZLE_64B
 };
@@ -870,9 +871,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   const bool is_mma = warp >= 4 * V3_WG;
   const int wg = is_mma ? warp - 4 * V3_WG : warp >> 2, wtid = tid & 127;
   int item = blockIdx.x;
+  const int seg = item % a.kv_segs; item /= a.kv_segs;          // key segment (1 unless key-segment mode)
   const int head = item % p.heads; item /= p.heads;
   const int win = item % a.n_win;
   const int b = item / a.n_win;
+  const int view0 = p.kv_view0 + seg * p.kvmap.views;           // first K/V view of this CTA
 
   if (tid == 0) {
 #pragma unroll
@@ -888,8 +891,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       const int X = win / a.k_ny, Y = win - X * a.k_ny;
       const int c1 = p.kvmap.grid ? Y : Y * p.kvmap.w2, c2 = p.kvmap.grid ? X : X * p.kvmap.w1;
       mbar_arrive_expect_tx(&bar_kv, (uint32_t)a.Lk * 128u);
-      tma_load_4d(sK, &a.tmK, &bar_kv, head * DH, c1, c2, b * p.kvmap.views);
-      tma_load_4d(sV, &a.tmV, &bar_kv, head * DH, c1, c2, b * p.kvmap.views);
+      tma_load_4d(sK, &a.tmK, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
+      tma_load_4d(sV, &a.tmV, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
     }
   }
   if (warp == 0) {
@@ -928,7 +931,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     if (tok < a.Lk) {
       const Tok t = token_of(p.kvmap, a.k_nx, a.k_ny, win, tok);
       if (t.in_range) {
-        const int64_t off = ((((int64_t)b * p.kvmap.views + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kv_stride + head * DH;
+        const int64_t off = ((((int64_t)b * a.kv_vt + view0 + t.n) * p.kvmap.Hv + t.py) * p.kvmap.Wv + t.px) * p.kv_stride + head * DH;
         srcK = kb_ + off * 2 + piece * 16;
         srcV = vb_ + off * 2 + piece * 16;
         nb = 16;
@@ -1118,6 +1121,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     // merge.  Otherwise o <- o / (l * passes) + earlier passes of this tile; the tile's last pass leaves
     // the sum in `o` (written out, or handed to the pass-split merge), the others park it in TMEM.
     auto finish_pass = [&](bool last_unit, float (&o)[DH]) {
+      if (p.part) {     // key-segment mode: un-normalised row + (max, sum) for cobevt_attn_merge; one pass per tile
+        const int qrow = (last_unit ? q_tile : q_tile - T) * TILE_Q + wtid;
+        if (qrow < rows_per_pass) {
+          float4* dst = reinterpret_cast<float4*>(p.part + seg * p.part_segment_stride +
+                                                  ((((int64_t)b * a.n_win + win) * p.heads + head) * a.Lq + qrow) * 36);
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) dst[ch] = make_float4(o[ch * 4 + 0], o[ch * 4 + 1], o[ch * 4 + 2], o[ch * 4 + 3]);
+          dst[8] = make_float4(m_fin, l_fin, 0.f, 0.f);
+        }
+        return;
+      }
       if (split_keys) return;
       const float inv = (l_fin > 0.f) ? inv_passes / l_fin : 0.f;
       const bool last_of_tile = last_unit || pj == 0;
@@ -1361,10 +1375,65 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   if (warp == 0) tmem_dealloc(tmem_base_s, 512);
 }
 
+// ---- merge of key-segment partials (see cobevt_attn_merge in the header) -----------------------------
+__global__ void attn_merge_kernel(const float* __restrict__ part, int S, int64_t seg_stride, uint16_t* __restrict__ out,
+                                  CobevtTokenMap qmap, int nx, int ny, int B, int n_win, int heads, int Lq,
+                                  int rows_per_pass, int passes, int q_mean, int out_stride, int bf16) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)B * n_win * heads * rows_per_pass;
+  if (idx >= total) return;
+  const int r = (int)(idx % rows_per_pass);
+  int64_t rest = idx / rows_per_pass;
+  const int head = (int)(rest % heads); rest /= heads;
+  const int win = (int)(rest % n_win);
+  const int b = (int)(rest / n_win);
+  float acc[DH];
+#pragma unroll
+  for (int d = 0; d < DH; ++d) acc[d] = 0.f;
+  for (int pass = 0; pass < passes; ++pass) {
+    const int t = pass * rows_per_pass + r;
+    const float* base = part + ((((int64_t)b * n_win + win) * heads + head) * Lq + t) * 36;
+    float M = -INFINITY;
+    for (int s = 0; s < S; ++s) M = fmaxf(M, base[s * seg_stride + 32]);
+    const float Ms = (M == -INFINITY) ? 0.f : M;
+    float L = 0.f, o[DH];
+#pragma unroll
+    for (int d = 0; d < DH; ++d) o[d] = 0.f;
+    for (int s = 0; s < S; ++s) {
+      const float4* ps = reinterpret_cast<const float4*>(base + s * seg_stride);
+      const float4 ml = ps[8];
+      const float w = fast_exp2(ml.x - Ms);
+      L = fmaf(ml.y, w, L);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float4 f = ps[ch];
+        o[ch * 4 + 0] = fmaf(f.x, w, o[ch * 4 + 0]); o[ch * 4 + 1] = fmaf(f.y, w, o[ch * 4 + 1]);
+        o[ch * 4 + 2] = fmaf(f.z, w, o[ch * 4 + 2]); o[ch * 4 + 3] = fmaf(f.w, w, o[ch * 4 + 3]);
+      }
+    }
+    const float inv = L > 0.f ? 1.0f / (L * (float)passes) : 0.f;
+#pragma unroll
+    for (int d = 0; d < DH; ++d) acc[d] = fmaf(o[d], inv, acc[d]);
+  }
+  const Tok t = token_of(qmap, nx, ny, win, r);
+  int64_t off;
+  if (q_mean) off = (((int64_t)b * qmap.Hv + t.py) * qmap.Wv + t.px) * out_stride + head * DH;
+  else off = ((((int64_t)b * qmap.views + t.n) * qmap.Hv + t.py) * qmap.Wv + t.px) * out_stride + head * DH;
+  uint4* op = reinterpret_cast<uint4*>(out + off);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    uint4 u;
+    u.x = pack_h2(acc[ch * 8 + 0], acc[ch * 8 + 1], bf16); u.y = pack_h2(acc[ch * 8 + 2], acc[ch * 8 + 3], bf16);
+    u.z = pack_h2(acc[ch * 8 + 4], acc[ch * 8 + 5], bf16); u.w = pack_h2(acc[ch * 8 + 6], acc[ch * 8 + 7], bf16);
+    op[ch] = u;
+  }
+}
+
 }  // namespace
 
+
 extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
-  if (!p || !p->q || !p->k || !p->v || !p->out) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: null pointer");
+  if (!p || !p->q || !p->k || !p->v || (!p->out && !p->part)) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: null pointer");
   const CobevtTokenMap& qm = p->qmap;
   const CobevtTokenMap& km = p->kvmap;
   if (qm.w1 <= 0 || qm.w2 <= 0 || km.w1 <= 0 || km.w2 <= 0 || qm.H % qm.w1 || qm.W % qm.w2 || km.H % km.w1 || km.W % km.w2)
@@ -1374,6 +1443,14 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   if ((p->k_pad == nullptr) != (p->v_pad == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: k_pad/v_pad must come together");
   AArgs a;
   a.p = *p;
+  a.kv_vt = p->kv_views_total > 0 ? p->kv_views_total : km.views;
+  a.kv_segs = p->kv_segments > 1 ? p->kv_segments : 1;
+  if (a.kv_segs > 1 && !p->part) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: kv_segments without part");
+  if (p->kv_view0 < 0 || p->kv_view0 + a.kv_segs * km.views > a.kv_vt) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: kv_view0 + kvmap.views exceeds kv_views_total");
+  if (p->part) {      // key-segment mode: every query token is a plain row, no bias (it is indexed by the full key set)
+    if (p->bias) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias in key-segment mode");
+    a.p.q_mean = 0;
+  }
   a.q_dbuf = 0;
   a.kv_tma = 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
@@ -1385,8 +1462,8 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.Lq = qm.views * qm.w1 * qm.w2;
   a.Lk = km.views * km.w1 * km.w2;
   a.n_chunks = cobevt::ceil_div(a.Lk, CHUNK);
-  a.q_passes = p->q_mean ? qm.views : 1;
-  const int rows = p->q_mean ? qm.w1 * qm.w2 : a.Lq;
+  a.q_passes = a.p.q_mean ? qm.views : 1;
+  const int rows = a.p.q_mean ? qm.w1 * qm.w2 : a.Lq;
   a.q_tiles = cobevt::ceil_div(rows, TILE_Q);
   a.C = p->heads * DH;
   if (a.p.q_stride == 0) a.p.q_stride = a.C;
@@ -1395,6 +1472,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   if (a.p.q_stride < a.C || a.p.kv_stride < a.C || a.p.out_stride < a.C || (a.p.q_stride | a.p.kv_stride | a.p.out_stride) % 8)
     return cobevt::fail(COBEVT_ERR_SHAPE, "attn: token strides must be >= heads*32 and multiples of 8");
   if (p->bias && p->q_mean) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias with q_mean");
+  if (p->part && !p->out) {}   // (out is ignored in key-segment mode)
   if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: dtype");
   const bool bf = p->dtype == COBEVT_BF16;
   a.idesc_qk = make_idesc_f16(128, CHUNK, bf, false, false);
@@ -1406,7 +1484,9 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH3) * CH3;
     const int smem = v3_fixed_smem() + keys_pad * (128 + 4);
-    if (smem <= 227 * 1024 && force_kernel != 2) {
+    if (p->part && !(smem <= 227 * 1024 && a.q_tiles >= 3))
+      return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: key-segment mode needs a resident segment (<= 704 keys) and >= 3 query tiles");
+    if (smem <= 227 * 1024 && (force_kernel != 2 || p->part)) {
       static int attr_v3[2] = {0, 0};
       auto kern = bf ? window_attn_v3_kernel<true> : window_attn_v3_kernel<false>;
       if (smem > attr_v3[bf]) {
@@ -1426,7 +1506,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
         if (!no_tma && enc && km.Hv == km.H && km.Wv == km.W && sx <= 8 && sy <= 8 && span_h <= 256 && span_w <= 256 &&
             km.views <= 256 && ((reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v)) & 15) == 0) {
           const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-          const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)km.Wv, (cuuint64_t)km.Hv, (cuuint64_t)p->B * km.views};
+          const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)km.Wv, (cuuint64_t)km.Hv, (cuuint64_t)p->B * a.kv_vt};
           const cuuint64_t strides[3] = {(cuuint64_t)a.p.kv_stride * 2, (cuuint64_t)km.Wv * a.p.kv_stride * 2,
                                          (cuuint64_t)km.Hv * km.Wv * a.p.kv_stride * 2};
           const cuuint32_t box[4] = {DH, (cuuint32_t)span_w, (cuuint32_t)span_h, (cuuint32_t)km.views};
@@ -1438,11 +1518,13 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
           a.kv_tma = (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) ? 1 : 0;
         }
       }
-      const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
+      const int64_t ctas = (int64_t)p->B * a.n_win * p->heads * a.kv_segs;
       kern<<<(unsigned)ctas, V3_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
       return cobevt::check_launch("window_attn_v3_kernel");
     }
   }
+  if (p->kv_view0 != 0 || a.kv_vt != km.views || a.kv_segs > 1)
+    return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: a K/V view subset needs the resident four-warpgroup kernel (<= 704 keys)");
   if (a.Lk <= KV_CAP_KEYS) {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
     a.q_dbuf = (v2_fixed_smem(1) + keys_pad * (128 + 4) <= 227 * 1024) ? 1 : 0;
@@ -1467,4 +1549,23 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   }
   window_attn_kernel<<<(unsigned)items, 128, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   return cobevt::check_launch("window_attn_kernel");
+}
+
+extern "C" int cobevt_attn_merge(const float* part, int32_t segments, int64_t segment_stride, void* out,
+                                 const CobevtTokenMap* qmap, int32_t B, int32_t heads, int32_t q_mean,
+                                 int32_t out_stride, int32_t dtype, void* stream) {
+  if (!part || !out || !qmap || segments <= 0 || B <= 0 || heads <= 0) return cobevt::fail(COBEVT_ERR_SHAPE, "attn_merge: bad args");
+  if (qmap->w1 <= 0 || qmap->w2 <= 0 || qmap->H % qmap->w1 || qmap->W % qmap->w2 || qmap->Hv != qmap->H || qmap->Wv != qmap->W)
+    return cobevt::fail(COBEVT_ERR_SHAPE, "attn_merge: bad query map");
+  if (dtype != COBEVT_F16 && dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn_merge: dtype");
+  const int nx = qmap->H / qmap->w1, ny = qmap->W / qmap->w2, n_win = nx * ny;
+  const int Lq = qmap->views * qmap->w1 * qmap->w2;
+  const int passes = q_mean ? qmap->views : 1;
+  const int rpp = q_mean ? qmap->w1 * qmap->w2 : Lq;
+  if (out_stride == 0) out_stride = heads * DH;
+  const int64_t total = (int64_t)B * n_win * heads * rpp;
+  attn_merge_kernel<<<(unsigned)((total + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      part, segments, segment_stride, reinterpret_cast<uint16_t*>(out), *qmap, nx, ny, B, n_win, heads, Lq, rpp, passes, q_mean,
+      out_stride, dtype == COBEVT_BF16 ? 1 : 0);
+  return cobevt::check_launch("attn_merge_kernel");
 }

@@ -191,6 +191,9 @@ def token_map(views, H, W, w1, w2, grid, Hv=None, Wv=None):
     return m
 
 
+RESIDENT_KEYS = 704     # keys one CTA of the four-warpgroup attention kernel keeps resident (csrc/window_attn.cu)
+
+
 def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_pad=None,
                      bias=None, key_mask=None):
     """q: (B, qviews, Hq, Wq, C); k, v: (B, kviews, Hk, Wk, C) 16-bit contiguous (valid extents).
@@ -215,6 +218,8 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     assert (qv, Hq, Wq) == (qmap.views, qmap.Hv, qmap.Wv)
     assert tuple(k.shape[1:4]) == (kvmap.views, kvmap.Hv, kvmap.Wv)
     out = torch.empty((B, Hq, Wq, C) if q_mean else (B, qv, Hq, Wq, C), dtype=q.dtype, device=q.device)
+    n_win = (qmap.H // qmap.w1) * (qmap.W // qmap.w2)
+    lq, lk = qmap.views * qmap.w1 * qmap.w2, kvmap.views * kvmap.w1 * kvmap.w2
     p = AttnParams()
     p.q, p.k, p.v, p.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
     p.k_pad, p.v_pad = _ptr(k_pad), _ptr(v_pad)
@@ -226,10 +231,30 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p.qmap, p.kvmap = qmap, kvmap
     p.B, p.heads, p.q_mean, p.scale, p.dtype = B, heads, 1 if q_mean else 0, scale, dtype_code(q.dtype)
     p.q_stride, p.kv_stride, p.out_stride = qs, ks, C
-    n_win = (qmap.H // qmap.w1) * (qmap.W // qmap.w2)
-    lq, lk = qmap.views * qmap.w1 * qmap.w2, kvmap.views * kvmap.w1 * kvmap.w2
-    with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32,
-                f"B={B} win={n_win} heads={heads} Lq={lq} Lk={lk} mean={int(bool(q_mean))} bias={bias is not None}"):
+    label = f"B={B} win={n_win} heads={heads} Lq={lq} Lk={lk} mean={int(bool(q_mean))} bias={bias is not None}"
+    # windows whose keys do not fit one resident pass: one call per group of K/V views (each a resident segment
+    # of the four-warpgroup kernel) + a log-sum-exp merge; e.g. the stage-2 global cross attention, 6 x 420 keys
+    per_view = kvmap.w1 * kvmap.w2
+    if (lk > RESIDENT_KEYS and kvmap.views > 1 and per_view <= RESIDENT_KEYS and lq > 2 * 128 and bias is None
+            and key_mask is None and k_pad is None and kvmap.Hv == kvmap.H and kvmap.Wv == kvmap.W):
+        vps = max(1, RESIDENT_KEYS // per_view)                  # views per segment
+        while kvmap.views % vps:                                 # equal segments -> ONE launch covers them all
+            vps -= 1
+        nseg = kvmap.views // vps
+        part = torch.empty((nseg, B, n_win, heads, lq, 36), dtype=torch.float32, device=q.device)
+        with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32, label + f" segs={nseg}"):
+            ps = AttnParams.from_buffer_copy(p)
+            ps.kvmap = token_map(vps, kvmap.H, kvmap.W, kvmap.w1, kvmap.w2, bool(kvmap.grid))
+            ps.out = None
+            ps.part = ctypes.c_void_p(part.data_ptr())
+            ps.kv_view0, ps.kv_views_total, ps.kv_segments = 0, kvmap.views, nseg
+            ps.part_segment_stride = part[0].numel()
+            _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(ps), _stream()), "cobevt_window_attn_fwd")
+            _lib.check(_lib.lib().cobevt_attn_merge(ctypes.c_void_p(part.data_ptr()), nseg, part[0].numel(), _ptr(out),
+                                                    ctypes.byref(qmap), B, heads, 1 if q_mean else 0, C,
+                                                    dtype_code(q.dtype), _stream()), "cobevt_attn_merge")
+        return out
+    with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32, label):
         _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
     return out
 

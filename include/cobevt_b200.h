@@ -112,9 +112,26 @@ typedef struct {
                          mean over n, fax_modules.py:243); 0: views are extra rows   */
   float scale;
   int32_t dtype;
+  /* --- key-segment mode (windows whose keys do not fit one resident pass, e.g. the stage-2 global
+   *     cross attention over 6 x 420 keys): the caller runs one call per group of K/V views and merges */
+  float* part;            /* NULL, or fp32 partial results of THIS call: (B, windows, heads, Lq, 36) =
+                             32 un-normalised output channels, running max (log2 domain), running sum, 2 pad;
+                             `out` is not written, q views are plain rows (q_mean is applied by the merge) */
+  int32_t kv_view0;       /* first view of the K/V tensors used by this call (kvmap.views = views used)   */
+  int32_t kv_views_total; /* views of the K/V tensors, i.e. their batch stride; 0: kvmap.views            */
+  int32_t kv_segments;    /* 0/1: one segment; n: ONE launch covers n consecutive segments of kvmap.views views
+                             each (starting at kv_view0), segment s writing to part + s * part_segment_stride */
+  int64_t part_segment_stride; /* in floats */
 } CobevtAttnParams;
 
 int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
+
+/* Merge `segments` partial results (consecutive at `segment_stride` floats) into the 16-bit output of the
+ * attention they partition: log-sum-exp across segments per query token, then the mean over query views when
+ * q_mean (fax_modules.py:243).  qmap / out layout as in cobevt_window_attn_fwd. */
+int cobevt_attn_merge(const float* part, int32_t segments, int64_t segment_stride, void* out,
+                      const CobevtTokenMap* qmap, int32_t B, int32_t heads, int32_t q_mean,
+                      int32_t out_stride, int32_t dtype, void* stream);
 
 /* ---------------------------------------------------------------------------
  * HBM-bound element-wise / gather kernels (dtype: 0 f16, 1 bf16; permute also 2 = f32)
