@@ -862,7 +862,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
   __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S F | O - | P - | Q0 Q1
   enum : uint32_t { BAR_S = 0, BAR_F = 8, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
-  __shared__ __align__(8) uint64_t bar_kv, bar_v;           // TMA path: K window landed / V window landed
+  __shared__ __align__(8) uint64_t bar_kv;                  // K / V windows landed (TMA path)
   __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
   __shared__ uint32_t tmem_base_s;
 
@@ -885,17 +885,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         mbar_init(&bars[i][j], j == 0 ? 1 : 128); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
       }
     mbar_init(&bar_kv, 1);
-    mbar_init(&bar_v, 1);
     mbar_fence_init();
     if (a.kv_tma) {
       // the whole key window of every view is one strided box: 2 instructions instead of 16 B per thread
       const int X = win / a.k_ny, Y = win - X * a.k_ny;
       const int c1 = p.kvmap.grid ? Y : Y * p.kvmap.w2, c2 = p.kvmap.grid ? X : X * p.kvmap.w1;
-      // (separate barriers: the first S = Q K^T only needs K; V lands under the first softmax)
-      mbar_arrive_expect_tx(&bar_kv, (uint32_t)a.Lk * 64u);
+      mbar_arrive_expect_tx(&bar_kv, (uint32_t)a.Lk * 128u);
       tma_load_4d(sK, &a.tmK, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
-      mbar_arrive_expect_tx(&bar_v, (uint32_t)a.Lk * 64u);
-      tma_load_4d(sV, &a.tmV, &bar_v, head * DH, c1, c2, b * a.kv_vt + view0);
+      tma_load_4d(sV, &a.tmV, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
     }
   }
   if (warp == 0) {
@@ -1027,7 +1024,6 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           next_qk();
         }
         mbar_wait(&bars[wg][4], (uint32_t)g & 1u);                  // P(g) written
-        if (g == 0 && a.kv_tma) mbar_wait(&bar_v, 0);               // V window landed
         tc_fence_after_sync();
         {                                                           // O (+)= P(g) V(chunk)
           const uint32_t va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
