@@ -73,17 +73,28 @@ struct KArgs {
 
 // exact (erf) GELU of the reference (nn.GELU default).  erf by Abramowitz-Stegun 7.1.26
 // (|abs err| <= 1.5e-7, far below the 16-bit output rounding) = 2 MUFU + ~10 FMA instead of erff's ~30.
-__device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));   // 1 MUFU, <= 1 ulp
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-z * z);
-  const float erf_abs = fmaf(-poly * t, e, 1.0f);          // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * erf_abs;              // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+// Evaluated on pairs: packed fp32 (FFMA2 / FMUL2) halves the issue slots of the polynomial; 4 MUFU per pair.
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  float z0, z1, t0, t1, p0, p1, q0, q1;
+  fmul2(z0, z1, a0, a1, 0.70710678118654752f, 0.70710678118654752f);
+  ffma2(t0, t1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(t1));
+  ffma2(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
+  ffma2(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+  ffma2(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+  ffma2(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+  fmul2(q0, q1, z0, z1, z0, z1);
+  fmul2(q0, q1, q0, q1, -1.4426950408889634f, -1.4426950408889634f);      // exp(-z^2) = 2^(-z^2 log2 e)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(q1));
+  fmul2(p0, p1, p0, p1, t0, t1);
+  fmul2(p0, p1, p0, p1, q0, q1);
+  float e0 = 1.0f - p0, e1 = 1.0f - p1;                                    // erf(|x| / sqrt 2)
+  fmul2(t0, t1, a0, a1, 0.5f, 0.5f);
+  fmul2(x0, x1, x0, x1, 0.5f, 0.5f);
+  ffma2(x0, x1, t0, t1, e0, e1, x0, x1);                                    // 0.5 x + 0.5 |x| erf
 }
 __device__ __forceinline__ uint32_t pack2(float a, float b, int bf16) {
   if (bf16) {
@@ -466,7 +477,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           for (int j = 0; j < U; ++j) v[j] = fmaxf(v[j], 0.f);
         } else if (p.act == COBEVT_ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < U; ++j) v[j] = gelu_erf(v[j]);
+          for (int j = 0; j < U; j += 2) gelu_erf2(v[j], v[j + 1]);
         }
         if (st_tma && p.y) {
           tma_out(&a.tmY, n0, relu_packed, v);
