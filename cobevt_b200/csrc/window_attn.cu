@@ -1,16 +1,20 @@
 // Windowed / dilated-grid multi-head attention (head_dim = 32) for sm_100a.
 //
-// One CTA (128 threads, one query row per thread) handles one
-// (batch row, window, head, 128-row query tile):
-//   S  = Q K^T          tcgen05.mma  M=128 N=128 K=32   (Q, K: K-major SWIZZLE_64B tiles)
-//   P  = softmax(...)   TMEM -> registers (tcgen05.ld), online max/sum in fp32, exp2 on MUFU,
-//                       P written as 16-bit K-major SWIZZLE_128B A-operand
-//   O += P V            tcgen05.mma  M=128 N=32  K=128  (V: MN-major SWIZZLE_64B, i.e. the
-//                       same row-per-key image as K -- no transpose)
-// Keys/values stream through a double-buffered 128-key chunk; window ('(x w1)(y w2)') and
-// grid ('(w1 x)(w2 y)') partitions are address arithmetic on the NHWC token maps, so none of
-// the reference's rearrange copies exist.  Zero-padded key positions use a constant token
+// Three kernels share the operand layouts (Q / K: K-major SWIZZLE_64B tiles, P: 16-bit K-major A operand, V: MN-major
+// SWIZZLE_64B, i.e. the same row-per-key image as K -- no transpose) and the token addressing: window
+// ('(x w1)(y w2)') and grid ('(w1 x)(w2 y)') partitions are address arithmetic / TMA boxes on the NHWC token maps,
+// so none of the reference's rearrange copies exist.  Zero-padded key positions use a constant token
 // (Linear(LayerNorm(0)) of the reference, survey quirk Q2).
+//
+//   window_attn_v3_kernel   windows of <= 704 keys (all FAX cross attentions of the north_star config and the
+//                           FuseBEVT window / grid attention): K/V resident, FOUR softmax warpgroups, O accumulated
+//                           in TMEM with lazy rescale, K/V by TMA; longer multi-view windows run as key segments
+//                           + cobevt_attn_merge.
+//   window_attn_v2_kernel   705 .. 1024 keys: K/V resident, two softmax warpgroups, register-level two-chunk pipeline.
+//   window_attn_kernel      anything longer: K/V streamed in 128-key chunks, one 128-thread CTA per query tile.
+//
+// Per chunk:  S = Q K^T (tcgen05.mma) -> TMEM -> registers (tcgen05.ld); online softmax in fp32 with exp2 on the
+// MUFU (scale * log2 e folded); P -> shared memory; O (+)= P V (tcgen05.mma).
 //
 // Reference: CrossWinAttention.forward fax_modules.py:198-248, partitions
 // fax_modules.py:399-433; Attention.forward fax_modules.py:132-176;
