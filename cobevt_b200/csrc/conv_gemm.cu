@@ -2,30 +2,31 @@
 //
 //   D[128 x BN] (TMEM, fp32) = A[128 x K] * B[BN x K]^T,   K = KH*KW*Cin
 //
-// One CTA per SM walks over output tiles (128 rows x BN channels).  Warp roles:
-//   warps 0-3  A producers   16-byte cp.async (zero-fill outside the image) into K-major
-//                            SWIZZLE_128B stages; 8 lanes per 128-byte channel run (coalesced)
-//   warps 4-11 epilogue      8 warps: TMEM lane quarter (warp % 4) x column half; one output row per
-//                            thread: all tcgen05.ld of the unit issued back to back, the accumulator
-//                            buffer is released as soon as it is in registers, then +bias (smem),
-//                            +residual (batched 16-byte loads), ReLU / GELU, optional row LayerNorm
-//                            second output (the two column halves exchange mean / M2 through smem),
-//                            16-bit / fp32 stores.  The accumulator is double-buffered in TMEM so
-//                            tile i's epilogue overlaps tile i+1's main loop
-//   warp  12   B loader      weights pre-packed on the host as ready SWIZZLE_128B tile images,
-//                            one cp.async.bulk (TMA engine) per k-block, or ALL k-blocks once when
-//                            they fit (resident weights: token GEMMs and 64-channel convs)
-//   warp  13   MMA issuer    one thread, tcgen05.mma M=128 N=BN K=16; tcgen05.commit frees stages
+// One CTA (20 warps) per SM walks over output tiles (128 rows x BN channels).  Warp roles:
+//   warps 4-11     epilogue team 0: TMEM lane quarter (warp % 4) x column half; one output row per thread: all
+//                  tcgen05.ld of the unit issued back to back, the accumulator is released as soon as it is in
+//                  registers, then +bias (smem), +residual, ReLU / exact GELU, optional row LayerNorm second output
+//                  (the two column halves exchange mean / M2 through smem); token GEMMs leave through a swizzled
+//                  staging tile + one TMA tensor store per warp, convs store 16 bytes per thread
+//   warps 0-3,     epilogue team 1 when the A operand comes from TMA (the teams take alternate tiles = alternate
+//         12-15    TMEM accumulators, 4 per CTA, 2 for BN = 256); otherwise warps 0-3 are the cp.async A producers
+//   warp  16       loader (one thread): weights pre-packed on the host as SWIZZLE_128B tile images by cp.async.bulk
+//                  -- ALL k-blocks once when they fit (resident weights) -- and the A ring by TMA tensor loads
+//   warp  17       MMA issuer: the whole warp walks the pipeline, the elected lane issues tcgen05.mma M=128 N=BN K=16
+//                  and the tcgen05.commit that frees stages / publishes accumulators
+//   warps 18-19    idle (they complete the control warpgroup for setmaxnreg: 104 registers for the 16 workers)
 //
-// A-operand modes
-//   GATHER  any conv: per 64-wide k-block the 128 x 64 im2col slice is gathered from the NHWC
-//           activation (no im2col buffer in HBM).
-//   HALO    3x3 / stride 1 / pad 1 / Cin % 64 == 0 (the bulk of the ResNet encoder): the output
-//           tile is 16 rows x 8 pixels; its 18 x 10 x 64ch input halo is loaded ONCE per 64-channel
-//           slab and all nine taps read it in place through shifted UMMA descriptors (start =
-//           slab + (ky*10+kx)*128 B, stride-byte-offset = 10*128 B).  The SWIZZLE_128B XOR is a
-//           function of absolute smem address bits (profiles/r01_umma_probe_halo.log), so shifted
-//           starts need no re-layout.  L2->SM traffic for A drops 9x vs the gather.
+// A-operand modes (host-selected, see cobevt_conv2d_nhwc_fwd)
+//   HALO    3x3 / stride 1 / pad 1 / Cin % 64 == 0 (the bulk of the ResNet encoder): the output tile is 16 rows x 8
+//           pixels; its 18 x 10 x 64ch input halo is ONE TMA box per 64-channel slab and all nine taps read it in
+//           place through shifted UMMA descriptors (start = slab + (ky*10+kx)*128 B, SBO = 10*128 B).  The
+//           SWIZZLE_128B XOR is a function of absolute smem address bits (profiles/r01_umma_probe_halo.log), so
+//           shifted starts need no re-layout.
+//   LINEAR  1x1 / stride 1 (every nn.Linear): one 2-D TMA box (128 rows x 64 channels) per k-block.
+//   TAP     other strides / kernel shapes with Cin in {8, 32, 64k}: one strided TMA box per filter tap.
+//   PATCH   8-channel input, stride_w = 1 (the stem): the unswizzled input patch is the A operand in place
+//           (overlapping 8 x 16 B core matrices, LBO = 16 B).
+//   GATHER  fallback: per-thread cp.async im2col slices (nearest-x2-upsampled inputs, odd channel counts).
 //
 // Replaces the cuDNN/cuBLAS calls behind torchvision ResNet (resnet_ms.py:46-89), the FAX
 // Bottleneck/downsample convs (fax_modules.py:472-489) and every nn.Linear of the token path
