@@ -606,7 +606,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             const int ty = t / a.tiles_x, tx = t - ty * a.tiles_x;
             mbar_wait(&a_empty[ps], pph);
             mbar_arrive_expect_tx(&a_full[ps], (uint32_t)(a.patch_w * a.patch_h * 16));
-            tma_load_4d(sA + ps * A_GATHER_BYTES, &a.tmap, &a_full[ps], 0, tx * TILE_W * p.stride_w - p.pad_w,
+            // (pixels and channels are one merged dimension, so a patch row is ONE 176-byte request, not 11)
+            tma_load_3d(sA + ps * A_GATHER_BYTES, &a.tmap, &a_full[ps], (tx * TILE_W * p.stride_w - p.pad_w) * 8,
                         ty * TILE_H * p.stride_h - p.pad_h, n);
             if (++ps == SA) { ps = 0; pph ^= 1u; }
           } else if (a.mode == MODE_TAP) {
@@ -696,11 +697,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           const uint32_t b_base = lo0 | (smem_u32(sB) >> 4);
           if (elect_one()) {
             if (do_mma) {
-              int j = 0;
-              for (int ky = 0; ky < p.KH; ++ky)
-                for (int kp = 0; kp < p.KW / 2; ++kp, ++j)
-                  umma_lohi(d_tmem, lo_p | ((a_addr + ky * pitch + kp * 32) >> 4), hi_p,
+              if (p.KH == 7 && p.KW == 4) {           // the stem: fully unrolled, descriptor deltas are immediates
+                const uint32_t a0 = lo_p | (a_addr >> 4), pstep = pitch >> 4;
+#pragma unroll
+                for (int j = 0; j < 14; ++j)
+                  umma_lohi(d_tmem, a0 + (j >> 1) * pstep + (j & 1) * 2, hi_p,
                             b_base + (j >> 2) * (kBStage >> 4) + (j & 3) * 2, hiB, idesc, j ? 1u : 0u);
+              } else {
+                int j = 0;
+                for (int ky = 0; ky < p.KH; ++ky)
+                  for (int kp = 0; kp < p.KW / 2; ++kp, ++j)
+                    umma_lohi(d_tmem, lo_p | ((a_addr + ky * pitch + kp * 32) >> 4), hi_p,
+                              b_base + (j >> 2) * (kBStage >> 4) + (j & 3) * 2, hiB, idesc, j ? 1u : 0u);
+              }
             }
             umma_commit(&a_empty[sa_]);
           }
@@ -819,11 +828,12 @@ bool make_a_tmap(KArgs& a) {
     r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (a.mode == MODE_PATCH) {
-    const cuuint64_t dims[4] = {(cuuint64_t)p.Cin, (cuuint64_t)p.Win, (cuuint64_t)p.Hin, (cuuint64_t)p.N};
-    const cuuint64_t strides[3] = {(cuuint64_t)p.Cin * 2, (cuuint64_t)p.Win * p.Cin * 2, (cuuint64_t)p.Hin * p.Win * p.Cin * 2};
-    const cuuint32_t box[4] = {8, (cuuint32_t)a.patch_w, (cuuint32_t)a.patch_h, 1};
-    const cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(&a.tmap, dt, 4, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    // {W*8, H, N}: the 8 channels and the pixels of an image row are one contiguous dimension
+    const cuuint64_t dims[3] = {(cuuint64_t)p.Win * 8, (cuuint64_t)p.Hin, (cuuint64_t)p.N};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.Win * 16, (cuuint64_t)p.Hin * p.Win * 16};
+    const cuuint32_t box[3] = {(cuuint32_t)a.patch_w * 8, (cuuint32_t)a.patch_h, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    r = enc(&a.tmap, dt, 3, const_cast<void*>(p.x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   } else if (a.mode == MODE_TAP) {
     // (fused filter rows: the KW taps of one row are KW*Cin contiguous elements starting at the pixel, i.e. a
@@ -1051,7 +1061,7 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
       // 8-channel inputs with unit stride along W: the raw input patch of a tile is the A operand (PATCH mode),
       // provided the whole packed weight can stay resident
       const int pw = TILE_W + p->KW - 1, ph = (TILE_H - 1) * p->stride_h + p->KH;
-      if (!(no_tap & 2) && p->Cin == 8 && p->stride_w == 1 && p->KW % 2 == 0 && pw <= 256 && ph <= 256 && pw * ph * 16 <= A_GATHER_BYTES &&
+      if (!(no_tap & 2) && p->Cin == 8 && p->stride_w == 1 && p->KW % 2 == 0 && pw * 8 <= 256 && ph <= 256 && pw * ph * 16 <= A_GATHER_BYTES &&
           a.n_tiles == 1 && (int64_t)a.KB * p->block_n * BLOCK_K * 2 <= 96 * 1024) {
         t.mode = MODE_PATCH;
         t.patch_w = pw;
