@@ -69,6 +69,8 @@ def lib():
         L.cobevt_conv2d_nhwc_fwd.argtypes = [ctypes.POINTER(ConvParams), c_vp]
         L.cobevt_window_attn_fwd.restype = ctypes.c_int
         L.cobevt_window_attn_fwd.argtypes = [ctypes.POINTER(AttnParams), c_vp]
+        L.cobevt_attn_resident_keys.restype = ctypes.c_int32
+        L.cobevt_attn_resident_keys.argtypes = []
         L.cobevt_attn_merge.restype = ctypes.c_int
         L.cobevt_attn_merge.argtypes = [c_vp, c_i32, ctypes.c_int64, c_vp, ctypes.POINTER(TokenMap), c_i32, c_i32, c_i32,
                                         c_i32, c_i32, c_vp]
@@ -107,5 +109,5 @@ def check(rc, what):
 
 EXPORTED_SYMBOLS = [
     "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
-    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge",
+    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys",
 ] + list(_ELTWISE_SIGS)

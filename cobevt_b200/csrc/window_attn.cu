@@ -1573,3 +1573,7 @@ extern "C" int cobevt_attn_merge(const float* part, int32_t segments, int64_t se
       out_stride, dtype == COBEVT_BF16 ? 1 : 0);
   return cobevt::check_launch("attn_merge_kernel");
 }
+
+extern "C" int32_t cobevt_attn_resident_keys(void) {
+  return ((227 * 1024 - v3_fixed_smem()) / (128 + 4)) / CH3 * CH3;
+}

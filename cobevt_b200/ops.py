@@ -191,7 +191,17 @@ def token_map(views, H, W, w1, w2, grid, Hv=None, Wv=None):
     return m
 
 
-RESIDENT_KEYS = 704     # keys one CTA of the four-warpgroup attention kernel keeps resident (csrc/window_attn.cu)
+
+
+_RESIDENT_KEYS = None
+
+
+def _resident_keys():
+    """Keys one CTA of the four-warpgroup attention kernel keeps resident (asked once from the library)."""
+    global _RESIDENT_KEYS
+    if _RESIDENT_KEYS is None:
+        _RESIDENT_KEYS = int(_lib.lib().cobevt_attn_resident_keys())
+    return _RESIDENT_KEYS
 
 
 def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_pad=None,
@@ -235,6 +245,7 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     # windows whose keys do not fit one resident pass: one call per group of K/V views (each a resident segment
     # of the four-warpgroup kernel) + a log-sum-exp merge; e.g. the stage-2 global cross attention, 6 x 420 keys
     per_view = kvmap.w1 * kvmap.w2
+    RESIDENT_KEYS = _resident_keys()
     if (lk > RESIDENT_KEYS and kvmap.views > 1 and per_view <= RESIDENT_KEYS and lq > 2 * 128 and bias is None
             and key_mask is None and k_pad is None and kvmap.Hv == kvmap.H and kvmap.Wv == kvmap.W):
         vps = max(1, RESIDENT_KEYS // per_view)                  # views per segment

@@ -126,6 +126,10 @@ typedef struct {
 
 int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
 
+/* Largest number of keys one call keeps resident per window on the four-warpgroup kernel (longer multi-view
+ * windows: key-segment mode above). */
+int32_t cobevt_attn_resident_keys(void);
+
 /* Merge `segments` partial results (consecutive at `segment_stride` floats) into the 16-bit output of the
  * attention they partition: log-sum-exp across segments per query token, then the mean over query views when
  * q_mean (fax_modules.py:243).  qmap / out layout as in cobevt_window_attn_fwd. */
