@@ -37,6 +37,20 @@ def test_version_and_error_string():
     assert L.cobevt_window_attn_fwd(ctypes.byref(a), None) == -1
 
 
+def test_attention_host_validation_and_capacity():
+    """Host-side checks of the attention entry points (no kernel is launched: every call fails validation)."""
+    from cobevt_b200 import _lib
+    L = _lib.lib()
+    cap = L.cobevt_attn_resident_keys()
+    assert cap > 0 and cap % 64 == 0 and cap >= 630          # the north_star windows (630 keys) must stay resident
+    a = _lib.AttnParams()
+    a.kv_segments = 3                                          # segments without a partial buffer / pointers
+    assert L.cobevt_window_attn_fwd(ctypes.byref(a), None) == -1
+    m = _lib.TokenMap()
+    assert L.cobevt_attn_merge(None, 2, 0, None, ctypes.byref(m), 1, 4, 0, 0, 0, None) == -1
+    assert b"attn_merge" in L.cobevt_last_error()
+
+
 def test_weight_packing_layout():
     """Packed image = [n_tile][k_block][row][64] with the SWIZZLE_128B chunk XOR."""
     import torch
