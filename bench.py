@@ -9,12 +9,17 @@ images) per GPU per step, fp16 storage / fp32 accumulation, synthetic weights an
   python bench.py --gpus 1 --steps K --warmup W              # our arm
   torchrun ... bench.py --gpus N ...                         # one rank per GPU (weak scaling)
   python bench.py --impl reference ...                       # CPU arm: the oracle port of the
-                                                             # reference forward on host cores
+                                                             # reference forward on the host cores
+  python bench.py --impl eager ...                           # the same torch-eager math on the GPU
+                                                             # (fp32 / TF32 / autocast-fp16): the
+                                                             # ">= 6x over PyTorch-eager" denominator
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput (CUDA events, max over
-ranks); `e2e` = same metric through CorpBEVT.forward with pinned-host inputs (H2D + D2H inside
+ranks); `e2e` = same metric through the module forward with pinned-host inputs (H2D + D2H inside
 the timed region); `roofline` = dominant kernel family (conv_gemm: implicit-GEMM conv/linear)
 algorithmic FLOP/s vs the measured bf16 peak; `roofline_attn` the same for the FAX attention
-kernel; `cpu_baseline` = the oracle on the host cores (bounded sample).
+kernel; `cpu_baseline` = the oracle on the host cores (bounded sample); `extra_configs` =
+BASELINE configs C2 / C3 / C5 timed the same way (N = 1 only); `shard_check` (N > 1) = the
+sharded output of this rank's samples compared bit for bit with a single-rank forward.
 """
 import argparse
 import copy
@@ -32,6 +37,8 @@ sys.path.insert(0, ROOT)
 
 SAMPLES_PER_GPU = 4
 AGENTS, CAMS = 5, 6
+METRIC = "BEV samples/sec (5-agent, 6-cam, 256x256 BEV)"
+WORKLOAD = "opv2v-corpbevt north_star: 5 agents x 6 cams x 224x480 -> 256x256 BEV"
 
 
 def peaks():
@@ -41,6 +48,42 @@ def peaks():
         return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d["bf16_tflops_sustained"],
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic():
+    """Per-launch DRAM traffic of the dominant kernels from the committed ncu --set full capture of this
+    command (profiles/r02_traffic.json, written by tools/ncu_summary.py); None when absent."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def host_info():
+    """(cores this process may really use, CPU model): the scheduler affinity, further limited by the cgroup CPU
+    quota (a container can see 128 CPUs and be throttled to a fraction of them)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    cores = max(1, min(cores, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    cores = max(1, min(cores, int(q / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    model = "unknown"
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return cores, model
 
 
 class ClockSampler:
@@ -87,33 +130,54 @@ def build_model(device):
     return model.to(device), cfg, sd
 
 
+# ------------------------------------------------------------------------------------------- CPU arm
 def cpu_baseline(cfg, sd, reps, warm):
-    """The oracle (fp32 port of the reference forward) on the host cores, bounded: ONE agent x 6
-    cameras of the north_star geometry per run (1/5 of a 5-agent sample; FuseBEVT still runs at
-    max_cav=5 with 4 padded slots), so a run is ~10-20 s instead of >60 s."""
+    """The oracle (fp32 port of the reference forward, pinned to the reference at 1e-5) on the host cores:
+    ONE full sample (5 agents x 6 cameras -> one BEV map) per run, `warm` warm-up runs, median of `reps`;
+    threads = the cores this process may run on (affinity), not os.cpu_count()."""
     from cobevt_b200 import synth
     from oracle import cobevt_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    cb = synth.synth_batch(cfg, record_len=(1,), n_cams=CAMS, seed=1)
+    cores, cpu_model = host_info()
+    cb = synth.synth_batch(cfg, record_len=(AGENTS,), n_cams=CAMS, seed=1)
     sd_cpu = {k: v.cpu() for k, v in sd.items()}
+    # thread count: eager torch on many-core hosts is often FASTER with fewer threads than cores (tiny ops, NUMA);
+    # give the CPU arm its best setting: time one agent's encoder + SinBEVT at a few counts and keep the fastest
+    cal = {}
+    one = synth.synth_batch(cfg, record_len=(1,), n_cams=CAMS, seed=1)
+    enc = cfg["encoder"]
     with torch.no_grad():
-        for _ in range(warm):
+        for t in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
+            torch.set_num_threads(t)
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                feats = orc.resnet_encoder(one["inputs"], sd_cpu, "encoder.", enc["num_layers"], enc["id_pick"])
+                orc.fax_module(feats, one["intrinsic"], one["extrinsic"], sd_cpu, "fax.", cfg["fax"])
+                dt1 = time.perf_counter() - t0
+                best = dt1 if best is None else min(best, dt1)
+            cal[t] = best
+    threads = min(cal, key=cal.get)
+    torch.set_num_threads(threads)
+    times = []
+    with torch.no_grad():
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
             orc.corpbevt(copy.deepcopy(cb), sd_cpu, cfg)
-        t0 = time.perf_counter()
-        for _ in range(reps):
-            orc.corpbevt(copy.deepcopy(cb), sd_cpu, cfg)
-        dt = (time.perf_counter() - t0) / reps
-    return {"value": (1.0 / AGENTS) / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "seconds_per_run": dt,
-            "sample": f"{reps} run(s) of ONE agent x {CAMS} cams (1/{AGENTS} of a sample, scaled), fp32 oracle, "
-                      f"{cores} torch threads, {warm} warm-up"}
+            if i >= warm:
+                times.append(time.perf_counter() - t0)
+    times.sort()
+    dt = times[len(times) // 2]
+    return {"value": 1.0 / dt, "unit": "samples/s", "cores": threads, "cores_available": cores, "cpu_model": cpu_model,
+            "kind": "port", "seconds_per_run": dt, "seconds_all_runs": times, "same_config": True,
+            "thread_calibration_s_per_agent": {str(k): v for k, v in cal.items()},
+            "sample": f"median of {reps} run(s) of ONE full sample ({AGENTS} agents x {CAMS} cams), fp32 oracle, "
+                      f"{threads} torch threads (fastest of {sorted(cal)} on a one-agent calibration; {cores} cores "
+                      f"available by affinity / cgroup quota), {warm} warm-up"}
 
 
 def run_reference(args):
-    """CPU arm: the oracle (port of the reference forward; the Python reference itself cannot
-    travel to the GPU box) on all host cores.  Each step is the bounded sample of
-    cpu_baseline(): one agent x 6 cameras = 1/5 of a 5-agent sample."""
+    """CPU arm: the oracle (port of the reference forward; the Python reference itself cannot travel to the
+    GPU box) on all host cores this process may use; a step = one full 5-agent sample."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -122,19 +186,182 @@ def run_reference(args):
     cfg = configs.north_star()
     model = cb.CorpBEVT(copy.deepcopy(cfg)).eval()
     sd = synth.synth_state_dict(model, seed=0)
-    steps = min(args.steps, 8)          # keep the whole run within a few minutes
-    base = cpu_baseline(cfg, sd, reps=steps, warm=1 if args.warmup else 0)
+    steps = max(1, min(args.steps, 5))          # keep the whole run within a few minutes
+    warm = 1 if args.warmup else 0
+    base = cpu_baseline(cfg, sd, reps=steps, warm=warm)
     val = base["value"]
     print(json.dumps({
-        "impl": "reference", "metric": "BEV samples/sec (5-agent, 6-cam, 256x256 BEV)", "value": val,
-        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": 1 if args.warmup else 0,
+        "impl": "reference", "metric": METRIC, "value": val,
+        "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": 1000 * base["seconds_per_run"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "opv2v-corpbevt north_star: 5 agents x 6 cams x 224x480 -> 256x256 BEV",
-                   "samples_per_step": 1.0 / AGENTS},
+        "config": {"workload": WORKLOAD, "samples_per_step": 1.0},
         "cpu_baseline": base,
         "e2e": {"value": val, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ------------------------------------------------------------------------------------------- eager-GPU arm
+def eager_gpu(cfg, sd, dev, samples=1, iters=5):
+    """The reference math in eager torch ON THE GPU (the oracle's plain torch ops: cuDNN convs, cuBLAS matmuls,
+    unfused softmax / LN / GELU) -- the denominator of the north_star's '>= 6x over PyTorch-eager'.  Three
+    precision settings; a setting that fails is reported as an error string."""
+    import contextlib
+    from cobevt_b200 import synth
+    from oracle import cobevt_oracle as orc
+    sdd = {k: v.to(dev) for k, v in sd.items()}
+    batch = synth.to_device(synth.synth_batch(cfg, record_len=(AGENTS,) * samples, n_cams=CAMS, seed=1), dev)
+    out = {}
+
+    def run(tag, tf32, ctx):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        try:
+            with torch.no_grad(), ctx:
+                for _ in range(2):
+                    orc.corpbevt(dict(batch), sdd, cfg)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    orc.corpbevt(dict(batch), sdd, cfg)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            out[tag] = {"samples_per_s": samples / ms * 1e3, "ms_per_step": ms}
+        except Exception as e:   # noqa: BLE001
+            out[tag] = {"error": repr(e)[:200]}
+
+    run("fp32", False, contextlib.nullcontext())
+    run("fp32_tf32", True, contextlib.nullcontext())
+    run("autocast_fp16", True, torch.autocast("cuda", dtype=torch.float16))
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = True
+    out["samples_per_step"] = samples
+    out["what"] = "oracle (reference math, pinned at 1e-5) as eager torch ops on this GPU, inputs resident"
+    return out
+
+
+def run_eager(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    _, cfg, sd = build_model("cpu")
+    eg = eager_gpu(cfg, sd, dev, samples=1, iters=max(1, min(args.steps, 10)))
+    best = eg.get("fp32", {})
+    val = best.get("samples_per_s")
+    print(json.dumps({
+        "impl": "eager", "metric": METRIC, "value": val, "unit": "samples/s", "n_gpus": 1, "steps": min(args.steps, 10),
+        "warmup": 2, "ms_per_step": best.get("ms_per_step"), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "samples_per_step": 1},
+        "eager_gpu": eg,
+    }))
+
+
+# ------------------------------------------------------------------------------------------- extra configs
+def _time_fn(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def extra_configs(dev):
+    """BASELINE configs beside the headline: C2 nuScenes SinBEVT (1 x 6 cams, 224x480, BEV 256, bf16), C3/C4
+    geometry OPV2V CoBEVT as corpbevt.yaml ships it (5 agents x 4 cams x 512x512, fp16), C5 the FuseBEVT block
+    micro-benchmark (window 8, C 128, H = W = 256, N agents 1..8).  CUDA-graph replay, inputs resident."""
+    import cobevt_b200 as cb
+    from cobevt_b200 import configs, synth, ops, nuscenes as ns
+    from cobevt_b200.parallel import _Graphed
+    out = {}
+    with torch.no_grad():
+        # ---- C2 ------------------------------------------------------------------------------------------
+        try:
+            cfg = configs.nuscenes_c2()
+            e = copy.deepcopy(cfg['encoder'])
+            for name, backbone in (("resnet34_levels", ns.ResNetFeatureBackbone(224, 480)),
+                                   ("efficientnet_b4_prefix", getattr(ns, "EfficientNetExtractor", None))):
+                if backbone is None:
+                    continue
+                if name == "efficientnet_b4_prefix":
+                    backbone = backbone(['reduction_2', 'reduction_3', 'reduction_4'], 224, 480)
+                enc = ns.PyramidAxialEncoder(backbone, e['cross_view'], e['cross_view_swap'], e['bev_embedding'],
+                                             e['self_attn'], e['dim'], e['middle'], e['scale'])
+                m = ns.CrossViewTransformer(enc, ns.Decoder(cfg['decoder_dim'], cfg['decoder_blocks'], True, 2),
+                                            cfg['dim_last'], copy.deepcopy(cfg['outputs'])).eval()
+                m.load_state_dict(synth.synth_state_dict(m, seed=0))
+                cb.set_compute_dtype(m, torch.bfloat16)
+                m = m.to(dev)
+                batch = synth.to_device(synth.synth_nuscenes_batch(224, 480, b=1, n_cams=6, seed=1), dev)
+                g = _Graphed(lambda image, intrinsics, extrinsics: m({'image': image, 'intrinsics': intrinsics,
+                                                                     'extrinsics': extrinsics})['bev'])
+                ms = _time_fn(lambda: g(batch['image'], batch['intrinsics'], batch['extrinsics']))
+                out["C2_nuscenes_sinbevt_bf16_" + name] = {"samples_per_s": 1e3 / ms, "ms_per_step": ms, "batch": 1,
+                                                           "cams": 6, "bev": 256, "dtype": "bf16"}
+        except Exception as ex:   # noqa: BLE001
+            out["C2_error"] = repr(ex)[:300]
+        # ---- C3 / C4 geometry ------------------------------------------------------------------------------
+        try:
+            cfg = configs.native_opv2v()
+            m = cb.CorpBEVT(copy.deepcopy(cfg)).eval()
+            m.load_state_dict(synth.synth_state_dict(m, seed=0))
+            m = m.to(dev)
+            S = 2
+            batch = synth.to_device(synth.synth_batch(cfg, record_len=(5,) * S, n_cams=4, seed=1), dev)
+            from cobevt_b200.parallel import ShardedCorpBEVT
+            sh = ShardedCorpBEVT(m, 0, 1, graphs=True)
+            ms = _time_fn(lambda: sh(batch, [5] * S, batch["transformation_matrix"]), iters=5)
+            x = sh.m.encode_nhwc(batch['inputs'], batch['intrinsic'], batch['extrinsic'])
+            rl = torch.tensor([5] * S, dtype=torch.int64, device=dev)
+            tm = batch["transformation_matrix"].float().contiguous()
+            gf = _Graphed(lambda tiles: m.fuse_nhwc(tiles, tm, rl)["dynamic_seg"])
+            ms_f = _time_fn(lambda: gf(x))
+            out["C3_opv2v_native_fp16"] = {"samples_per_s": S * 1e3 / ms, "ms_per_step": ms, "samples_per_step": S,
+                                           "agents": 5, "cams": 4, "image": 512, "bev": 256, "dtype": "f16",
+                                           "fusebevt_decoder_head_only_ms": ms_f,
+                                           "fusebevt_decoder_head_only_samples_per_s": S * 1e3 / ms_f}
+            del m, sh, gf
+        except Exception as ex:   # noqa: BLE001
+            out["C3_error"] = repr(ex)[:300]
+        # ---- C5 --------------------------------------------------------------------------------------------
+        try:
+            rows = []
+            for N in (1, 2, 3, 4, 5, 6, 7, 8):
+                blk = cb.SwapFusionBlockMask(128, 256, 32, 8, N, 0.0).eval()
+                blk.load_state_dict(synth.synth_state_dict(blk, seed=0))
+                blk = blk.to(dev)
+                x = torch.randn(N * 256 * 256, 128, device=dev).half()
+                mask = torch.ones(1, 256, 256, N, dtype=torch.uint8, device=dev)
+                plan = blk.plan()
+                for _ in range(2):
+                    plan.run(x, None, (1, N, 256, 256, 128), mask)
+                torch.cuda.synchronize()
+                ops.STATS.reset()
+                ops.STATS.profile = True
+                plan.run(x, None, (1, N, 256, 256, 128), mask)
+                torch.cuda.synchronize()
+                ops.STATS.profile = False
+                fam = ops.STATS.family_ms()
+                att_ms, att_fl = fam.get("window_attn", 0.0), ops.STATS.flops["window_attn"]
+                T = 64 * N
+                exps = 2 * 4 * 1024 * T * T
+                io = 2 * 4 * N * 65536 * 128 * 2                   # q,k,v read + out write, two attentions
+                rows.append({"n_agents": N, "block_ms": sum(fam.values()), "attn_ms": att_ms,
+                             "attn_tflops": att_fl / att_ms / 1e9, "attn_texp_per_s": exps / att_ms / 1e9,
+                             "attn_min_io_gbs": io / att_ms / 1e6})
+                ops.STATS.reset()
+            out["C5_fusebevt_block_w8_256"] = rows
+        except Exception as ex:   # noqa: BLE001
+            out["C5_error"] = repr(ex)[:300]
+    return out
 
 
 def main():
@@ -142,20 +369,23 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "eager"])
     ap.add_argument("--layout", default=None, choices=["aligned", "straddle"],
                     help="N>1: 'straddle' (default) offsets sample boundaries so agents of one sample land on "
                          "different ranks and the NCCL all-gather runs; 'aligned' needs no collective")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2 / C3 / C5 configs and the eager-GPU proxy")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.impl == "eager":
+        return run_eager(args)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
     from cobevt_b200 import ops, synth
-    from cobevt_b200.parallel import ShardedCorpBEVT, row_shard
+    from cobevt_b200.parallel import ShardedCorpBEVT, row_shard, sample_shard
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -177,7 +407,12 @@ def main():
     total_rows = sum(record_len)
     r0, r1 = row_shard(total_rows, world, rank)
     rows = r1 - r0
-    g_batch = synth.synth_batch(dict(cfg, max_cav=rows), record_len=(rows,), n_cams=CAMS, seed=1 + rank)
+
+    def rank_batch(r):
+        a, b = row_shard(total_rows, world, r)
+        return synth.synth_batch(dict(cfg, max_cav=b - a), record_len=(b - a,), n_cams=CAMS, seed=1 + r)
+
+    g_batch = rank_batch(rank)
     host = {k: g_batch[k].pin_memory() for k in ("inputs", "intrinsic", "extrinsic")}
     devb = {k: v.to(dev) for k, v in host.items()}
     tm_all = synth.synth_batch(cfg, record_len=tuple(record_len), n_cams=1, seed=99)["transformation_matrix"].to(dev)
@@ -277,6 +512,36 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     out_bytes = SAMPLES_PER_GPU * 2 * 256 * 256 * 4
 
+    # ---- N > 1: the sharded result of the samples this rank owns, bit-compared with a single-rank forward ------
+    shard_check = None
+    if world > 1:
+        s0, s1 = sample_shard(len(record_len), world, rank)
+        starts = [0]
+        for n in record_len:
+            starts.append(starts[-1] + n)
+        cache = {rank: g_batch}
+        pieces = {k: [] for k in ("inputs", "intrinsic", "extrinsic")}
+        for grow in range(starts[s0], starts[s1]):
+            owner = next(r for r in range(world) if row_shard(total_rows, world, r)[0] <= grow < row_shard(total_rows, world, r)[1])
+            if owner not in cache:
+                cache[owner] = rank_batch(owner)
+            loc = grow - row_shard(total_rows, world, owner)[0]
+            for k in pieces:
+                pieces[k].append(cache[owner][k][loc:loc + 1])
+        with torch.no_grad():
+            got = sharded(devb, record_len, tm_all)["dynamic_seg"].clone()
+            single = {k: torch.cat(v, 0).to(dev) for k, v in pieces.items()}
+            single["record_len"] = torch.tensor(record_len[s0:s1], dtype=torch.int64, device=dev)
+            single["transformation_matrix"] = tm_all[s0:s1].contiguous()
+            want = model(single)["dynamic_seg"]
+        torch.cuda.synchronize()
+        diff = (got - want).abs().max()
+        flag = torch.tensor([1.0 if torch.equal(got, want) else 0.0, -diff.item()], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        shard_check = {"bit_equal_all_ranks": bool(flag[0].item() == 1.0), "max_abs_diff": float(-flag[1].item()),
+                       "samples_checked_per_rank": s1 - s0,
+                       "what": "sharded (all-gather) output of the samples each rank owns vs a single-rank forward of the same rows"}
+
     # ---- per-family device time (CUDA events around every launch, same process, after the run) --
     ops.STATS.reset()
     ops.STATS.profile = True
@@ -290,13 +555,17 @@ def main():
     fam_n = {k: v // psteps for k, v in ops.STATS.launches.items()}
     ops.STATS.profile = False
     pk = peaks()
+    traffic = ncu_traffic()
 
     def roof(fam):
         tf = fam_fl[fam] / (fam_ms[fam] * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": fam, "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": tf / pk["tf_sustained"], "peak_source": pk["source"] + " bf16 sustained",
+                "frac": tf / pk["tf_sustained"], "frac_of_burst_peak": tf / pk["tf_burst"],
+                "peak_source": pk["source"] + " bf16 sustained (kernels timed back to back inside a 10 ms step)",
                 "launches_per_step": fam_n[fam], "ms_per_step": fam_ms[fam],
-                "algorithmic_gflop_per_step": fam_fl[fam] / 1e9, "traffic": None}
+                "algorithmic_gflop_per_step": fam_fl[fam] / 1e9,
+                "timing": "CUDA events around every launch of an eagerly launched step (not the graph replay)",
+                "traffic": traffic.get(fam)}
 
     if rank != 0:
         if world > 1:
@@ -305,17 +574,16 @@ def main():
         return
 
     result = {
-        "metric": "BEV samples/sec (5-agent, 6-cam, 256x256 BEV)", "value": value, "unit": "samples/s",
+        "metric": METRIC, "value": value, "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "opv2v-corpbevt north_star: 5 agents x 6 cams x 224x480 -> 256x256 BEV "
-                               "(ResNet34 levels 1-3 -> SinBEVT/FAX -> STTF -> FuseBEVT -> decoder -> head)",
+        "config": {"workload": WORKLOAD + " (ResNet34 levels 1-3 -> SinBEVT/FAX -> STTF -> FuseBEVT -> decoder -> head)",
                    "samples_per_gpu_per_step": SAMPLES_PER_GPU, "agent_rows_per_gpu": rows,
                    "images_per_gpu_per_step": rows * CAMS,
                    "parallelism": f"agent-rows dp{world}, layout={layout}, "
                                   f"allgather={'on' if (world > 1 and layout == 'straddle') else 'off'}",
                    "l2": f"inputs {h2d / 1e6:.0f} MB per step > 126 MB L2 (no flush needed)",
-                   "launch": "eager" if args.no_graphs else "CUDA graphs (encode + fuse), kernels identical to eager"},
+                   "launch": "eager" if args.no_graphs else f"CUDA graph ({sharded.mode}), kernels identical to eager"},
         "clocks": clocks,
         "e2e": {"value": n_equiv * args.steps / (ms_e2e / 1000.0), "unit": "samples/s",
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": out_bytes, "ms_per_step": ms_e2e / args.steps,
@@ -324,14 +592,25 @@ def main():
         "roofline": roof("conv_gemm"),
         "roofline_attn": roof("window_attn"),
         "family_ms_per_step": fam_ms,
+        "family_ms_note": "per-family times are CUDA-event timed around eagerly launched kernels (they include launch gaps "
+                          "the graph replay removes, so their sum exceeds ms_per_step)",
         "algorithmic_gflop_per_sample": sum(fam_fl.values()) / 1e9 / SAMPLES_PER_GPU,
     }
+    if shard_check is not None:
+        result["shard_check"] = shard_check
     tot_tf = sum(fam_fl.values()) / 1e12 * world * args.steps / (ms / 1000.0)
     result["roofline_whole_step"] = {"achieved": tot_tf / world, "unit": "TFLOP/s per GPU",
                                      "frac": tot_tf / world / pk["tf_sustained"]}
 
+    if world == 1 and not args.no_extras:
+        del slots, sharded
+        torch.cuda.empty_cache()
+        result["extra_configs"] = extra_configs(dev)
+        result["eager_gpu"] = eager_gpu(cfg, sd, dev, samples=1, iters=5)
+        if "samples_per_s" in result["eager_gpu"].get("fp32", {}):
+            result["eager_gpu"]["speedup_vs_fp32_eager"] = value / result["eager_gpu"]["fp32"]["samples_per_s"]
     if world == 1 and not args.no_cpu_baseline:
-        result["cpu_baseline"] = cpu_baseline(cfg, sd, reps=1, warm=0)
+        result["cpu_baseline"] = cpu_baseline(cfg, sd, reps=3, warm=1)
     print(json.dumps(result))
     if world > 1:
         dist.barrier()

@@ -7,7 +7,7 @@ loads cobevt_b200/libcobevt_sm100.so and fails loudly if it is missing.
 from .modules import (  # noqa: F401
     ResnetEncoder, BEVEmbedding, Attention, CrossWinAttention, CrossViewSwapAttention, FAXModule,
     SwapFusionEncoder, SwapFusionBlock, SwapFusionBlockMask, NaiveDecoder, BevSegHead, STTF,
-    CorpBEVT, FaxFusedTransformer, Bottleneck,
+    CorpBEVT, FaxFusedTransformer, Bottleneck, NaiveCompressor, post_process, set_compute_dtype,
 )
 
 __version__ = "0.1.0"

@@ -98,6 +98,13 @@ _ELTWISE_SIGS = {
     "cobevt_mean_views_ln": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp],
     "cobevt_sttf_regroup": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_i32, c_i32, c_vp],
     "cobevt_permute": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_stage_rgb_u8": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp],
+    "cobevt_softmax_argmax": [c_vp, c_vp, c_vp, c_i32, c_i32, c_i64, c_vp],
+    "cobevt_resize_nearest": [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_vp],
+    "cobevt_dwconv_swish": [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                            c_i32, c_i32, c_vp],
+    "cobevt_se_gate": [c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp],
+    "cobevt_scale_channels": [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp],
 }
 
 

@@ -26,6 +26,32 @@ inline int check_launch(const char* what) {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Function attributes (max dynamic smem) and the SM count are PER DEVICE: caches are indexed by the current device.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int num_sms() {
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    sms[dev] = v > 0 ? v : 148;
+  }
+  return sms[dev];
+}
+
+// Timing-experiment knobs (COBEVT_CONV_DEBUG / COBEVT_ATTN_DEBUG produce WRONG results by design) exist only in
+// builds made with -DCOBEVT_DEBUG_KNOBS; the release library compiles them out.
+#ifdef COBEVT_DEBUG_KNOBS
+#define COBEVT_DBG(args, bit) ((args).dbg & (bit))
+#else
+#define COBEVT_DBG(args, bit) false
+#endif
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point table (nullptr if unavailable)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           for (int i = 0; i < 8; ++i) {
             const int r = r0 + 16 * i;
             const bool ok = kvalid && (m0 + r) < a.M;
-            if (!(a.dbg & 2)) cp_async16(dst + sw128_off(r, c8), ok ? src + r * row_bytes : xbytes, ok ? 16u : 0u);
+            if (!COBEVT_DBG(a, 2)) cp_async16(dst + sw128_off(r, c8), ok ? src + r * row_bytes : xbytes, ok ? 16u : 0u);
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
         }
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             const bool ok = kvalid && iy >= 0 && iy < Hlog && ix >= 0 && ix < Wlog;
             if (p.in_upsample) { iy >>= 1; ix >>= 1; }
             const int64_t off = ((int64_t)(pixbase[i] + iy * p.Win + ix) * p.Cin + coff) * 2;
-            if (!(a.dbg & 2)) cp_async16(dst + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
+            if (!COBEVT_DBG(a, 2)) cp_async16(dst + sw128_off(r, c8), ok ? xbytes + off : xbytes, ok ? 16u : 0u);
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
         }
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             if (pix < HALO_H * HALO_W) {
               const bool ok = poff[i] >= 0;
               const int64_t off = ((int64_t)(ok ? poff[i] : 0) + slab * 64 + chunk * 8) * 2;
-              if (!(a.dbg & 2)) cp_async16(dst + pix * 128 + ((chunk ^ (pix & 7)) << 4), xbytes + (ok ? off : 0), ok ? 16u : 0u);
+              if (!COBEVT_DBG(a, 2)) cp_async16(dst + pix * 128 + ((chunk ^ (pix & 7)) << 4), xbytes + (ok ? off : 0), ok ? 16u : 0u);
             }
           }
           cp_async_mbar_arrive_noinc(&a_full[s]);   // async arrival when this stage's bytes have landed
@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
         continue;
       }
-      if (a.dbg & 8) {   // profiling experiment: no TMEM read / math at all
+      if (COBEVT_DBG(a, 8)) {   // profiling experiment: no TMEM read / math at all
         tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       // (inner box = U * 2 bytes: SWIZZLE_128B / 64B / 32B) and leaves as one tensor store (full lines, clipped
       // at the tensor bounds, no store instructions or address arithmetic in this warp).
       const uint32_t stg = smem_u32(sStage) + (uint32_t)(team * 8 + e) * STG_WARP_BYTES;
-      const bool st_tma = a.st_tma && !(a.dbg & 1);
+      const bool st_tma = a.st_tma && !COBEVT_DBG(a, 1);
       auto tma_out = [&](const CUtensorMap* tm, int n0c, bool relu, const float (&vv)[U]) {
         constexpr int CH16 = U / 8;                     // 16-byte pieces per row
         constexpr int RPL = 128 / (U * 2);              // rows per 128-byte line
@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
           __syncwarp();
           if (lane == 0) mbar_arrive(&acc_empty[buf]);
         }
-        const bool live = row_ok && n0 < p.Cout && !(a.dbg & 1);
+        const bool live = row_ok && n0 < p.Cout && !COBEVT_DBG(a, 1);
         float v[U];
         {
           const float4* b4 = reinterpret_cast<const float4*>(sBias + (n0 & 511));   // broadcast LDS.128
@@ -479,6 +479,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         } else if (p.act == COBEVT_ACT_GELU) {
 #pragma unroll
           for (int j = 0; j < U; j += 2) gelu_erf2(v[j], v[j + 1]);
+        } else if (p.act == COBEVT_ACT_SWISH) {        // x * sigmoid(x): MBConv expand / stem (efficientnet_pytorch Swish)
+#pragma unroll
+          for (int j = 0; j < U; ++j) v[j] = __fdividef(v[j], 1.0f + __expf(-v[j]));
         }
         if (st_tma && p.y) {
           tma_out(&a.tmY, n0, relu_packed, v);
@@ -675,7 +678,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
       const uint64_t tA_n = make_smem_desc(0, 2048, 128, LAYOUT_NONE);
       const uint32_t hiA_64 = (uint32_t)(tA_64 >> 32), hiA_n = (uint32_t)(tA_n >> 32), lo_n = (uint32_t)tA_n;
       const uint32_t idesc = a.idesc;
-      const bool do_mma = !(a.dbg & 4);
+      const bool do_mma = !COBEVT_DBG(a, 4);
       if (a.resident_b) mbar_wait(&b_res_full, 0);
       for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
         const int buf = acc_it & (NACC - 1);
@@ -811,7 +814,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-int g_num_sms = 0;
 
 // tensor map of the A operand for the TMA-fed modes; returns false if the layout cannot be described
 bool make_a_tmap(KArgs& a) {
@@ -933,19 +935,15 @@ int launch(KArgs& a, cudaStream_t st) {
   }
   if (a.st_tma) smem += 16 * STG_WARP_BYTES;
   if (a.mode == MODE_PATCH && !a.resident_b) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: PATCH mode needs the resident weight image");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[cobevt::kMaxDevices] = {false};      // per device (and per BN: one static per instantiation)
+  const int dev = cobevt::current_device();
+  if (!attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "conv: set smem attr: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr_set[dev] = true;
   }
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
-  }
-  const int grid = a.total_tiles < g_num_sms ? a.total_tiles : g_num_sms;
+  const int num_sms = cobevt::num_sms();
+  const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
   conv_gemm_kernel<BN><<<grid, NUM_THREADS, (size_t)smem, st>>>(a);
   return cobevt::check_launch("conv_gemm_kernel");
 }
@@ -1072,7 +1070,9 @@ extern "C" int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream) {
     }
   }
   a.total_tiles = a.m_tiles * a.n_tiles;
+#ifdef COBEVT_DEBUG_KNOBS
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_CONV_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+#endif
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (p->block_n) {
     case 16: return launch<16>(a, st);

@@ -76,17 +76,21 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
   }
 }
 
-// Unbounded variant for the innermost loops of kernels whose protocol is covered by the bounded waits
-// elsewhere (three instructions per retry; try_wait itself suspends the thread in hardware).
+// Lean variant for the innermost loops: the retry counter lives only inside the asm block (no live register across
+// the loop body), try_wait itself suspends the thread in hardware, and a protocol bug still traps instead of hanging.
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parity) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
       "WAIT_%=:\n\t"
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
       "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, %2;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "trap;\n\t"
       "DONE_%=:\n\t}"
-      ::"r"(bar_addr), "r"(parity)
+      ::"r"(bar_addr), "r"(parity), "n"(COBEVT_MBAR_SPIN_LIMIT)
       : "memory");
 }
 

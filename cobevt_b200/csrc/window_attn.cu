@@ -44,6 +44,7 @@ struct AArgs {
   int32_t q_nx, q_ny, k_nx, k_ny;  // windows along h / w
   uint32_t idesc_qk, idesc_pv;
   int32_t kv_vt, kv_segs;             // views of the K/V tensors (batch stride in views); key segments per launch
+  int32_t bias_ld;                    // keys per bias row = keys of the WHOLE window (all segments); == Lk without segments
   int32_t kv_tma;                     // resident K / V windows are fetched by two 4-D TMA tensor loads
   alignas(64) CUtensorMap tmK, tmV;   // {C, Wv, Hv, B*views}, box {32, w2 (span), w1 (span), views}, SWIZZLE_64B
 };
@@ -76,6 +77,29 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// exp2 on the FMA / ALU pipes for a pair of logits (FA-4 style software exponential): the MUFU does 16 ex2 per
+// clock per SM, which bounds this head size (128 tensor FLOPs per exponential), so a compile-time share of every
+// chunk's exponentials is evaluated here instead.  x = i + f (i = floor, by an add with round-to-minus-infinity
+// against 1.5 * 2^23, which also leaves i in the low mantissa bits); 2^f by the degree-3 minimax polynomial
+// (max relative error 8.8e-5, a fifth of the fp16 rounding P receives anyway); 2^i by adding i to the exponent field.
+// Inputs are clamped to >= -126 (masked keys arrive as -inf): the result is then a normal number <= 2^-126 * 2,
+// which the 16-bit P rounds to zero exactly like the MUFU path.
+__device__ __forceinline__ void poly_exp2_pair(float& x0, float& x1) {
+  x0 = fmaxf(x0, -126.0f);
+  x1 = fmaxf(x1, -126.0f);
+  float t0, t1, r0, r1, f0, f1, p0, p1;
+  asm("{\n\t.reg .b64 a, b, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %4};\n\t"
+      "add.rm.ftz.f32x2 d, a, b;\n\tmov.b64 {%0, %1}, d;\n\t}"
+      : "=f"(t0), "=f"(t1) : "f"(x0), "f"(x1), "f"(12582912.0f));
+  fadd2(r0, r1, t0, t1, -12582912.0f, -12582912.0f);                 // floor(x) as a float (exact)
+  ffma2(f0, f1, r0, r1, -1.0f, -1.0f, x0, x1);                        // f = x - floor(x) in [0, 1)
+  ffma2(p0, p1, f0, f1, 0.077119089663028717f, 0.077119089663028717f, 0.227564394474029541f, 0.227564394474029541f);
+  ffma2(p0, p1, p0, p1, f0, f1, 0.695146143436431885f, 0.695146143436431885f);
+  ffma2(p0, p1, p0, p1, f0, f1, 1.0f, 1.0f);
+  x0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  x1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
 }
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b, int bf16) {
@@ -451,7 +475,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
   uint8_t* sQ = sQ_all + wg * (1 + q_dbuf) * SQ_BYTES;
   uint8_t* sP = sP_all + wg * 2 * SP2_BYTES;
   const int rows_per_pass = p.q_mean ? p.qmap.w1 * p.qmap.w2 : a.Lq;
-  const int n_my_tiles = ((a.dbg & 8) && wg == 1) ? 0 : (a.q_tiles - wg + 1) >> 1;      // tiles wg, wg+2, ...
+  const int n_my_tiles = (COBEVT_DBG(a, 8) && wg == 1) ? 0 : (a.q_tiles - wg + 1) >> 1;      // tiles wg, wg+2, ...
   const int NP = n_my_tiles * a.q_passes;                // passes of this warpgroup
   const int total = NP * n_ch;                           // chunks of this warpgroup
 
@@ -708,7 +732,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
         ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
         ffma2(x[j + 4], x[j + 5], x[j + 4], x[j + 5], es, es, nm, nm);
         ffma2(x[j + 6], x[j + 7], x[j + 6], x[j + 7], es, es, nm, nm);
-        if (!(a.dbg & 1)) {
+        if (!COBEVT_DBG(a, 1)) {
 #pragma unroll
           for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
         }
@@ -716,7 +740,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
-        if (!(a.dbg & 2))
+        if (!COBEVT_DBG(a, 2))
         sts128((p_swz ^ ((uint32_t)cc << 4)) + PAR * SP2_BYTES,
                pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
                pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
@@ -751,7 +775,7 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
       exps8(6);
       exps8(7);
       l_run = l_run * alpha_cur + ((sm[0] + sm[1]) + (sm[2] + sm[3]));
-      if (!(a.dbg & 4)) fence_proxy_async_smem();
+      if (!COBEVT_DBG(a, 4)) fence_proxy_async_smem();
       tc_fence_before_sync();
       mbar_arrive_a(bar_wg + BAR_P + PAR * 8);
       tmem_ld_wait();                       // ro has landed
@@ -851,9 +875,11 @@ constexpr int V3_WG = 4;
 constexpr int V3_THREADS = (V3_WG + 1) * 128;            // 640
 constexpr int V3_REGS_SOFTMAX = 112, V3_REGS_ISSUER = 32;   // the CTA pool is 640 x 96 = 61440 = 16*32*112 + 4*32*32
 constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 16 KB: one P buffer per warpgroup
+constexpr int V3_POLY_DEFAULT = 2;
 __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + SP3_BYTES); }
 
-template <bool BF16>
+// POLY: bit cc set -> the 8 exponentials of 8-key group cc (of the 8 groups of a 64-key chunk) use poly_exp2_pair
+template <bool BF16, int POLY>
 __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __grid_constant__ AArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -866,7 +892,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
   __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S F | O - | P - | Q0 Q1
   enum : uint32_t { BAR_S = 0, BAR_F = 8, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
-  __shared__ __align__(8) uint64_t bar_kv;                  // K / V windows landed (TMA path)
+  __shared__ __align__(8) uint64_t bar_k, bar_v;            // K / V windows landed (TMA path): S = Q K^T starts as soon as K
+                                                            // is in, the V window keeps streaming under the first softmax
   __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
   __shared__ uint32_t tmem_base_s;
 
@@ -888,15 +915,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       for (int j = 0; j < 2; ++j) {
         mbar_init(&bars[i][j], j == 0 ? 1 : 128); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
       }
-    mbar_init(&bar_kv, 1);
+    mbar_init(&bar_k, 1);
+    mbar_init(&bar_v, 1);
     mbar_fence_init();
     if (a.kv_tma) {
       // the whole key window of every view is one strided box: 2 instructions instead of 16 B per thread
       const int X = win / a.k_ny, Y = win - X * a.k_ny;
       const int c1 = p.kvmap.grid ? Y : Y * p.kvmap.w2, c2 = p.kvmap.grid ? X : X * p.kvmap.w1;
-      mbar_arrive_expect_tx(&bar_kv, (uint32_t)a.Lk * 128u);
-      tma_load_4d(sK, &a.tmK, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
-      tma_load_4d(sV, &a.tmV, &bar_kv, head * DH, c1, c2, b * a.kv_vt + view0);
+      mbar_arrive_expect_tx(&bar_k, (uint32_t)a.Lk * 64u);
+      tma_load_4d(sK, &a.tmK, &bar_k, head * DH, c1, c2, b * a.kv_vt + view0);
+      mbar_arrive_expect_tx(&bar_v, (uint32_t)a.Lk * 64u);
+      tma_load_4d(sV, &a.tmV, &bar_v, head * DH, c1, c2, b * a.kv_vt + view0);
     }
   }
   if (warp == 0) {
@@ -976,7 +1005,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   const int n_uch = split_keys ? (n_ch > sub ? (n_ch - sub + G - 1) / G : 0) : n_ch;   // chunks per pass
   const int c_first = split_keys ? sub : 0, c_step = split_keys ? G : 1;
   const int NP = n_my_tiles * passes_per_tile;
-  const int total = ((a.dbg & 8) && wg > 0) ? 0 : NP * n_uch;
+  const int total = (COBEVT_DBG(a, 8) && wg > 0) ? 0 : NP * n_uch;
 
   if (is_mma) {
     // =============================== MMA issuer of warpgroup `wg` ===========================
@@ -1001,7 +1030,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
             ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
       };
-      if (a.kv_tma) mbar_wait(&bar_kv, 0);
+      if (a.kv_tma) mbar_wait(&bar_k, 0);
       int gq = 0, Pq = 0, kq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
       auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T
         if (kq == 0) {
@@ -1028,6 +1057,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           next_qk();
         }
         mbar_wait(&bars[wg][4], (uint32_t)g & 1u);                  // P(g) written
+        if (g == 0 && a.kv_tma) mbar_wait(&bar_v, 0);               // the V window has landed
         tc_fence_after_sync();
         {                                                           // O (+)= P(g) V(chunk)
           const uint32_t va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
@@ -1049,7 +1079,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     const float sl2 = p.scale * 1.4426950408889634f;
     const float L2E = 1.4426950408889634f;
     const bool any_mask = p.key_mask != nullptr;
-    const bool bias_vec = (a.Lk & 3) == 0;
+    const bool bias_vec = ((a.Lk | a.bias_ld) & 3) == 0;
+    const int bias_k0 = view0 * (p.kvmap.w1 * p.kvmap.w2);     // first key of this CTA's views within the whole window
     const uint32_t p_swz = (smem_u32(sP) + (uint32_t)wtid * 128u) | (((uint32_t)wtid & 7u) << 4);          // SW128 row
     const uint32_t bar_wg = smem_u32(&bars[wg][0]);
     const uint32_t km_s = smem_u32(kmask);
@@ -1217,7 +1248,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         }
         const int qrow = q_tile * TILE_Q + wtid;
         if (p.bias && qrow < rows_per_pass) {
-          const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.Lk + key0;
+          const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.bias_ld + bias_k0 + key0;
           if (bias_vec && key0 + CH3 <= a.Lk) {
 #pragma unroll
             for (int j = 0; j < CH3 / 4; ++j) {
@@ -1271,8 +1302,13 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         ffma2(x[j + 2], x[j + 3], x[j + 2], x[j + 3], es, es, nm, nm);
         ffma2(x[j + 4], x[j + 5], x[j + 4], x[j + 5], es, es, nm, nm);
         ffma2(x[j + 6], x[j + 7], x[j + 6], x[j + 7], es, es, nm, nm);
+        if ((POLY >> cc) & 1) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
+          for (int t = 0; t < 8; t += 2) poly_exp2_pair(x[j + t], x[j + t + 1]);
+        } else {
+#pragma unroll
+          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
+        }
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
@@ -1451,13 +1487,16 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.kv_segs = p->kv_segments > 1 ? p->kv_segments : 1;
   if (a.kv_segs > 1 && !p->part) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: kv_segments without part");
   if (p->kv_view0 < 0 || p->kv_view0 + a.kv_segs * km.views > a.kv_vt) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: kv_view0 + kvmap.views exceeds kv_views_total");
-  if (p->part) {      // key-segment mode: every query token is a plain row, no bias (it is indexed by the full key set)
-    if (p->bias) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias in key-segment mode");
+  if (p->part) {      // key-segment mode: every query token is a plain row; bias rows span the keys of ALL K/V views
     a.p.q_mean = 0;
   }
+  a.bias_ld = a.kv_vt * km.w1 * km.w2;
   a.q_dbuf = 0;
   a.kv_tma = 0;
+  a.dbg = 0;
+#ifdef COBEVT_DEBUG_KNOBS
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
+#endif
   a.q_nx = qm.H / qm.w1; a.q_ny = qm.W / qm.w2;
   a.k_nx = km.H / km.w1; a.k_ny = km.W / km.w2;
   a.n_win = a.q_nx * a.q_ny;
@@ -1491,8 +1530,17 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     if (p->part && !(smem <= 227 * 1024 && a.q_tiles >= 3))
       return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: key-segment mode needs a resident segment (<= 704 keys) and >= 3 query tiles");
     if (smem <= 227 * 1024 && (force_kernel != 2 || p->part)) {
-      static int attr_v3[2] = {0, 0};
-      auto kern = bf ? window_attn_v3_kernel<true> : window_attn_v3_kernel<false>;
+      static int attr_v3_dev[cobevt::kMaxDevices][4][2] = {};        // per device, per kernel instance
+      int* attr_v3 = nullptr;
+      // share of the exponentials evaluated on the FMA pipes: COBEVT_ATTN_POLY = 0 none, 1 = 2/8, 2 = 3/8 (default), 3 = 4/8
+      static int poly_sel = -1;
+      if (poly_sel < 0) { const char* e = getenv("COBEVT_ATTN_POLY"); poly_sel = e ? atoi(e) : V3_POLY_DEFAULT; if (poly_sel < 0 || poly_sel > 3) poly_sel = V3_POLY_DEFAULT; }
+      typedef void (*KernT)(const AArgs);
+      static const KernT kerns[2][4] = {
+          {window_attn_v3_kernel<false, 0x00>, window_attn_v3_kernel<false, 0x44>, window_attn_v3_kernel<false, 0x92>, window_attn_v3_kernel<false, 0xAA>},
+          {window_attn_v3_kernel<true, 0x00>, window_attn_v3_kernel<true, 0x44>, window_attn_v3_kernel<true, 0x92>, window_attn_v3_kernel<true, 0xAA>}};
+      KernT kern = kerns[bf][poly_sel];
+      attr_v3 = attr_v3_dev[cobevt::current_device()][poly_sel];
       if (smem > attr_v3[bf]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
@@ -1533,7 +1581,8 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
     a.q_dbuf = (v2_fixed_smem(1) + keys_pad * (128 + 4) <= 227 * 1024) ? 1 : 0;
     const int smem = v2_fixed_smem(a.q_dbuf) + keys_pad * (128 + 4);
-    static int attr_v2[2] = {0, 0};
+    static int attr_v2_dev[cobevt::kMaxDevices][2] = {{0, 0}};
+    int* attr_v2 = attr_v2_dev[cobevt::current_device()];
     auto kern = bf ? window_attn_v2_kernel<true> : window_attn_v2_kernel<false>;
     if (smem > attr_v2[bf]) {
       cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1545,7 +1594,8 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     kern<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
     return cobevt::check_launch("window_attn_v2_kernel");
   }
-  static bool attr_set = false;
+  static bool attr_set_dev[cobevt::kMaxDevices] = {false};
+  bool& attr_set = attr_set_dev[cobevt::current_device()];
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(window_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));

@@ -13,7 +13,7 @@ Folding done at plan time (all exact re-associations of the reference math):
 import torch
 
 from . import ops
-from .ops import PackedConv, ACT_NONE, ACT_RELU, ACT_GELU
+from .ops import PackedConv, ACT_NONE, ACT_RELU, ACT_GELU, ACT_SWISH
 
 LN_EPS = 1e-5
 
@@ -84,15 +84,16 @@ class ResNetPlan:
                 blocks.append((convs, ds))
             self.levels.append(blocks)
 
-    def run(self, images, nchw=False, mean=None, std=None):
-        """images (NI, H, W, 3) [or (NI, 3, H, W) with nchw] fp32 -> list of NHWC 16-bit feature maps."""
+    def run(self, images, nchw=False, mean=None, std=None, bgr=False):
+        """images (NI, H, W, 3) [or (NI, 3, H, W) with nchw] fp32, or uint8 camera frames (then x/255, optional
+        BGR->RGB and (x - mean) / std happen in the staging kernel) -> list of NHWC 16-bit feature maps."""
         if nchw:
             N, _, H, W = images.shape
         else:
             N, H, W, _ = images.shape
         OH, OW = (H + 6 - 7) // 2 + 1, (W + 6 - 7) // 2 + 1
         Hp, Wp = max(H + 6, 2 * OH + 5), (max(W + 6, 2 * OW + 6) + 1) // 2 * 2
-        x = ops.pack_rgb4_padded(images, self.dtype, 3, 3, Hp, Wp, nchw=nchw, mean=mean, std=std).view(N, Hp, Wp // 2, 8)
+        x = ops.pack_rgb4_padded(images, self.dtype, 3, 3, Hp, Wp, nchw=nchw, mean=mean, std=std, bgr=bgr).view(N, Hp, Wp // 2, 8)
         x, _, _ = ops.conv2d_nhwc(x, self.stem, stride=(2, 1), pad=0, act=ACT_RELU, out_hw=(OH, OW))
         x = ops.maxpool3x3s2(x)
         feats = []
@@ -322,37 +323,65 @@ class SwapAttnPlan:
         self.f2 = PackedConv(ff[3].weight.detach().float(), ff[3].bias.detach().float(), device, dtype)
 
 
+class SwapBlockPlan:
+    """One SwapFusionBlockMask / SwapFusionBlock (swap_fusion_modules.py:131-230): window attention + FFN, then
+    grid attention + FFN, both PreNormResidual; the partitions are addressing inside the attention kernel."""
+
+    def __init__(self, blk, use_mask, ws, device, dtype):
+        self.use_mask, self.ws = use_mask, ws
+        if use_mask:
+            pairs = [(blk.window_attention, blk.window_ffd), (blk.grid_attention, blk.grid_ffd)]
+        else:
+            pairs = [(blk.block[1], blk.block[2]), (blk.block[5], blk.block[6])]
+        self.pairs = [SwapAttnPlan(a, f, device, dtype) for a, f in pairs]
+
+    def run(self, x, x_ln, dims, mask):
+        """x (B*L*H*W, d) residual stream, x_ln its plain LayerNorm (or None) -> (x, x_ln) after the block."""
+        B, L, H, W, d = dims
+        if x_ln is None:
+            x_ln = ops.layernorm_rows(x)
+        for kind, sp in enumerate(self.pairs):
+            qkv = ops.linear_tokens(x_ln, sp.qkv)[0].view(B, L, H, W, 3 * d)
+            m = ops.token_map(L, H, W, self.ws, self.ws, kind == 1)
+            a = ops.window_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], m, m, sp.heads, sp.scale,
+                                     False, bias=sp.bias, key_mask=mask if self.use_mask else None)
+            x, _, x_ln = ops.linear_tokens(a.reshape(-1, d), sp.out, res=x, ln_out=True)
+            hmid = ops.linear_tokens(x_ln, sp.f1, act=ACT_GELU)[0]
+            x, _, x_ln = ops.linear_tokens(hmid, sp.f2, res=x, ln_out=True)
+        return x, x_ln
+
+
 class FusionPlan:
     """SwapFusionEncoder (swap_fusion_modules.py:233-286)."""
 
     def __init__(self, enc, device, dtype):
         self.use_mask = enc.mask
         self.ws = enc.window_size
-        self.blocks = []
-        for blk in enc.layers:
-            if enc.mask:
-                pairs = [(blk.window_attention, blk.window_ffd), (blk.grid_attention, blk.grid_ffd)]
-            else:
-                pairs = [(blk.block[1], blk.block[2]), (blk.block[5], blk.block[6])]
-            self.blocks.append([SwapAttnPlan(a, f, device, dtype) for a, f in pairs])
+        self.blocks = [SwapBlockPlan(blk, enc.mask, enc.window_size, device, dtype) for blk in enc.layers]
         self.head = PackedConv(*fold_ln_linear(enc.mlp_head[2], enc.mlp_head[3]), device, dtype)
 
     def run(self, x, mask):
         """x (B, L, H, W, d) 16-bit; mask (B, H, W, L) uint8 or None -> (B, H, W, d)."""
         B, L, H, W, d = x.shape
         x = x.reshape(-1, d)
-        x_ln = ops.layernorm_rows(x)
+        x_ln = None
         for blk in self.blocks:
-            for kind, sp in enumerate(blk):
-                qkv = ops.linear_tokens(x_ln, sp.qkv)[0].view(B, L, H, W, 3 * d)
-                m = ops.token_map(L, H, W, self.ws, self.ws, kind == 1)
-                a = ops.window_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], m, m, sp.heads, sp.scale,
-                                         False, bias=sp.bias, key_mask=mask if self.use_mask else None)
-                x, _, x_ln = ops.linear_tokens(a.reshape(-1, d), sp.out, res=x, ln_out=True)
-                hmid = ops.linear_tokens(x_ln, sp.f1, act=ACT_GELU)[0]
-                x, _, x_ln = ops.linear_tokens(hmid, sp.f2, res=x, ln_out=True)
+            x, x_ln = blk.run(x, x_ln, (B, L, H, W, d), mask)
         m_ln = ops.mean_views_ln(x.view(B, L, H * W, d))
         return ops.linear_tokens(m_ln, self.head)[0].view(B, H, W, d)
+
+
+class CompressorPlan:
+    """NaiveCompressor (naive_compress.py:5-28): three conv3x3 + BatchNorm(eps 1e-3) + ReLU."""
+
+    def __init__(self, m, device, dtype):
+        self.convs = [PackedConv(*fold_conv_bn(c, b), device, dtype)
+                      for c, b in ((m.encoder[0], m.encoder[1]), (m.decoder[0], m.decoder[1]), (m.decoder[3], m.decoder[4]))]
+
+    def run(self, x):
+        for pc in self.convs:
+            x, _, _ = ops.conv2d_nhwc(x, pc, pad=1, act=ACT_RELU)
+        return x
 
 
 # --------------------------------------------------------------------------- decoder / head
@@ -378,8 +407,9 @@ class SegHeadPlan:
     def __init__(self, head, device, dtype):
         self.target = head.target
         mk = lambda c: PackedConv(c.weight.detach().float(), c.bias.detach().float(), device, dtype)
-        self.dyn = mk(head.dynamic_head) if head.target in ("dynamic", "both") else None
-        self.sta = mk(head.static_head) if head.target in ("static", "both") else None
+        # bev_seg_head.py:35-61: 'dynamic' -> dynamic head only, 'static' -> static head only, anything else -> both
+        self.dyn = mk(head.dynamic_head) if head.target != "static" else None
+        self.sta = mk(head.static_head) if head.target != "dynamic" else None
 
     def run(self, x, b, l):
         """x (b*l, H, W, C) -> dict of (b, l, classes, H, W) fp32 (bev_seg_head.py:35-61)."""
@@ -468,3 +498,88 @@ class LogitsPlan:
         y, _, _ = ops.conv2d_nhwc(y, self.a, pad=1, act=ACT_RELU)
         _, z32, _ = ops.conv2d_nhwc(y, self.b, want16=False, out32=True)
         return ops.nhwc_to_nchw(z32, torch.float32)
+
+
+# --------------------------------------------------------------------------- EfficientNet-B4 prefix (MBConv)
+def static_same_pad(size, k, s):
+    """(before, after) padding of efficientnet_pytorch's Conv2dStaticSamePadding for the NOMINAL extent `size`."""
+    out = -(-size // s)
+    pad = max((out - 1) * s + k - size, 0)
+    return pad // 2, pad - pad // 2
+
+
+class MBConvPlan:
+    """One MBConvBlock (efficientnet_pytorch 0.7.1) with eval BatchNorm (eps 1e-3) folded: 1x1 expand + swish on the
+    tensor-core GEMM, depthwise kxk + swish + squeeze sums, squeeze-excite gate, gate application, 1x1 project
+    (+ identity skip in the epilogue)."""
+
+    def __init__(self, blk, k, stride, expand, cin, cout, nominal, device, dtype):
+        self.k, self.stride, self.skip = k, stride, (stride == 1 and cin == cout)
+        self.pad = static_same_pad(nominal, k, stride)
+        self.expand = None
+        if expand != 1:
+            self.expand = PackedConv(*fold_conv_bn(blk._expand_conv, blk._bn0), device, dtype)
+        wd, bd = fold_conv_bn(blk._depthwise_conv, blk._bn1)                      # (C, 1, k, k)
+        self.wd = _dev_f32(wd[:, 0].permute(1, 2, 0), device)                      # (k, k, C)
+        self.bd = _dev_f32(bd, device)
+        self.w1 = _dev_f32(blk._se_reduce.weight.flatten(1), device)
+        self.b1 = _dev_f32(blk._se_reduce.bias, device)
+        self.w2 = _dev_f32(blk._se_expand.weight.flatten(1), device)
+        self.b2 = _dev_f32(blk._se_expand.bias, device)
+        self.project = PackedConv(*fold_conv_bn(blk._project_conv, blk._bn2), device, dtype)
+
+    def run(self, x):
+        N, H, W, _ = x.shape
+        y = x
+        if self.expand is not None:
+            y = ops.conv2d_nhwc(y, self.expand, act=ACT_SWISH)[0]
+        C = y.shape[-1]
+        pb, pa = self.pad
+        OH, OW = (H + pb + pa - self.k) // self.stride + 1, (W + pb + pa - self.k) // self.stride + 1
+        sums = torch.zeros(N, C, dtype=torch.float32, device=x.device)
+        y = ops.dwconv_swish(y, self.wd, self.bd, self.k, self.stride, pb, pb, OH, OW, sums=sums)
+        gate = ops.se_gate(sums, OH * OW, self.w1, self.b1, self.w2, self.b2)
+        ops.scale_channels_(y, gate)
+        return ops.conv2d_nhwc(y, self.project, res=x if self.skip else None)[0]
+
+
+class EffNetPlan:
+    """stem (3x3 s2 static-same conv + BN + swish on RGBx super-pixels) + the MBConv groups of
+    nuscenes/cross_view_transformer/model/backbones/efficientnet.py:56-69."""
+
+    def __init__(self, ext, device, dtype):
+        self.dtype = dtype
+        nominal = ext.nominal_image_size
+        w, b = fold_conv_bn(ext.layers[0][0], ext.layers[0][1])                 # (48, 3, 3, 3)
+        co = w.shape[0]
+        # 2 pixels x 4 channels = one 16-byte super-pixel (see ResNetPlan): kernel row = 2 super-taps, stride (2, 1)
+        wp = torch.zeros(co, 4, 3, 4)
+        wp[:, :3, :, :3] = w
+        wp = wp.reshape(co, 4, 3, 2, 2).permute(0, 4, 1, 2, 3)                   # co dx c ky kxs
+        self.stem = PackedConv(wp.reshape(co, 8, 3, 2), b, device, dtype)
+        self.stem.k_alg = 27
+        self.stem_pad = static_same_pad(nominal, 3, 2)
+        nominal = -(-nominal // 2)
+        self.groups = []
+        for gi, spec in enumerate(ext.block_specs):
+            blocks = []
+            for j, (k, s, e, cin, cout) in enumerate(spec):
+                blocks.append(MBConvPlan(ext.layers[gi + 1][j], k, s, e, cin, cout, nominal, device, dtype))
+                nominal = -(-nominal // s)
+            self.groups.append(blocks)
+
+    def run(self, images_nchw, mean=None, std=None):
+        """images (N, 3, H, W) fp32 -> list of NHWC 16-bit group outputs."""
+        N, _, H, W = images_nchw.shape
+        pb, pa = self.stem_pad
+        OH, OW = (H + pb + pa - 3) // 2 + 1, (W + pb + pa - 3) // 2 + 1
+        Hp, Wp = max(H + pb, 2 * OH + 1), max(W + pb, 2 * OW + 2)
+        Wp += Wp & 1
+        x = ops.pack_rgb4_padded(images_nchw, self.dtype, pb, pb, Hp, Wp, nchw=True, mean=mean, std=std).view(N, Hp, Wp // 2, 8)
+        x = ops.conv2d_nhwc(x, self.stem, stride=(2, 1), pad=0, act=ACT_SWISH, out_hw=(OH, OW))[0]
+        feats = []
+        for blocks in self.groups:
+            for blk in blocks:
+                x = blk.run(x)
+            feats.append(x)
+        return feats

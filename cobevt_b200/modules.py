@@ -6,8 +6,12 @@ the sm_100a kernels through ``engine``/``ops``.  Parameters are ordinary fp32
 ``nn.Parameter``s; folded/packed 16-bit weight images are derived caches ("plans") rebuilt
 after ``load_state_dict`` / device moves and never saved.
 
-Inference only: a forward in training mode, with autograd enabled on parameters that
-require grad, or on a non-CUDA tensor raises -- there is no CPU or eager fallback.
+Inference only: a forward in training mode or on a non-CUDA tensor raises -- there is no CPU or
+eager fallback.  The kernels record no autograd graph: outputs are plain (detached) tensors
+whether or not grad mode is on, exactly like a forward under ``torch.no_grad()``.
+
+Shape violations raise what the reference raises: ``einops.EinopsError`` where the reference's
+``rearrange`` would reject a non-divisible window, ``AssertionError`` where it asserts.
 
 Reference classes mirrored (paths under opv2v/opencood/models):
   backbones/resnet_ms.py ResnetEncoder :8-89; sub_modules/fax_modules.py BEVEmbedding :38-90,
@@ -26,6 +30,27 @@ import torch.nn as nn
 from . import engine, ops
 
 COMPUTE_DTYPE = torch.float16
+
+
+def _einops_error(msg):
+    """The exception type the reference's einops.rearrange raises for a non-divisible partition."""
+    try:
+        from einops import EinopsError
+    except Exception:                      # einops absent: its error derives from RuntimeError
+        return RuntimeError(msg)
+    return EinopsError(msg)
+
+
+def set_compute_dtype(module, dtype):
+    """Select the 16-bit storage / tensor-core operand type (torch.float16 or torch.bfloat16; fp32
+    accumulation either way) for every kernel-backed sub-module of ``module``; plans are rebuilt lazily."""
+    if dtype not in (torch.float16, torch.bfloat16):
+        raise TypeError(f"compute dtype must be float16 or bfloat16, got {dtype}")
+    for m in module.modules():
+        if isinstance(m, _Planned):
+            m.compute_dtype = dtype
+            object.__setattr__(m, "_plan", None)
+    return module
 
 
 def _require_inference(mod, *tensors):
@@ -77,12 +102,14 @@ class _BasicBlock(nn.Module):
         self.downsample = downsample
 
 
-class Bottleneck(nn.Module):
-    """Parameter layout of torchvision.models.resnet.Bottleneck (v1.5: stride on conv2)."""
+class Bottleneck(_Planned):
+    """torchvision.models.resnet.Bottleneck (v1.5: stride on conv2) as the FAX stages use it
+    (fax_modules.py:10,472: ``Bottleneck(c, c // 4)``, stride 1, identity shortcut)."""
     expansion = 4
 
     def __init__(self, cin, planes, stride=1, downsample=None):
         super().__init__()
+        self.stride = stride
         self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
         self.bn1 = nn.BatchNorm2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
@@ -91,6 +118,17 @@ class Bottleneck(nn.Module):
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.relu = nn.ReLU(inplace=True)
         self.downsample = downsample
+
+    def _build_plan(self, dev, dt):
+        return engine.BottleneckPlan(self, dev, dt)
+
+    def forward(self, x):
+        """x (N, C, H, W) -> (N, C, H, W)."""
+        _require_inference(self, x)
+        if self.stride != 1 or self.downsample is not None:
+            raise NotImplementedError("only the stride-1 identity-shortcut Bottleneck of the FAX stages is on the kernel path")
+        y = self.plan().run(ops.nchw_to_nhwc(x, self.compute_dtype))
+        return ops.nhwc_to_nchw(y, torch.float32)
 
 
 _RESNET_CFG = {18: (_BasicBlock, (2, 2, 2, 2)), 34: (_BasicBlock, (3, 4, 6, 3)),
@@ -134,9 +172,15 @@ class ResnetEncoder(_Planned):
         self.idx_pick = params['id_pick']
         if self.num_layers not in _RESNET_CFG:
             raise ValueError("{} is not a valid number of resnet layers".format(self.num_layers))
+        if self.num_layers not in (18, 34):
+            raise ValueError(f"ResNet-{self.num_layers} needs Cout up to 2048; the sm_100a conv kernel serves Cout <= 512 "
+                             "(BasicBlock ResNet-18/34, the depths the shipped configs use)")
         if self.pretrained:
             raise RuntimeError("pretrained=True needs a weight download; load a checkpoint with load_state_dict")
         self.encoder = _ResNetTrunk(self.num_layers)
+        # uint8 camera frames: when forward() receives a uint8 tensor the RgbPreProcessor arithmetic
+        # (rgb_preprocessor.py:16-36: optional BGR->RGB, /255, (x - mean) / std) runs inside the stem's staging kernel
+        self.input_mean, self.input_std, self.input_bgr = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225), False
         h, w = params['image_height'], params['image_width']
         shapes = []
         for li, c in enumerate(self.encoder.level_channels):
@@ -154,6 +198,9 @@ class ResnetEncoder(_Planned):
         """engine-level entry: list (per level, up to the deepest picked) of (B*L*M, h, w, C)."""
         _require_inference(self, input_images)
         b, l, m, h, w, c = input_images.shape
+        if input_images.dtype == torch.uint8:
+            return self.plan().run(input_images.reshape(b * l * m, h, w, c).contiguous(), mean=self.input_mean,
+                                   std=self.input_std, bgr=self.input_bgr)
         return self.plan().run(input_images.reshape(b * l * m, h, w, c).float().contiguous())
 
     def forward(self, input_images):
@@ -243,7 +290,7 @@ class CrossWinAttention(_Planned):
         assert k.shape == v.shape
         b, n, X, Y, W1, W2, d = q.shape
         _, nk, x_, y_, w1, w2, _ = k.shape
-        assert X * Y == x_ * y_
+        assert X * Y == x_ * y_           # fax_modules.py:208 (q_height * q_width == kv_height * kv_width)
         pl, dt = self.plan(), self.compute_dtype
         tok = lambda t: t.permute(0, 2, 3, 1, 4, 5, 6).reshape(-1, t.shape[1], t.shape[4], t.shape[5], d).to(dt).contiguous()
         qt, kt, vt = tok(q), tok(k), tok(v)                                  # (b*X*Y, n, W1, W2, d)
@@ -301,6 +348,9 @@ class CrossViewSwapAttention(_Planned):
             object.__setattr__(self, "_plan", None)
         b, n, c, h, w = feature.shape
         dt = self.compute_dtype
+        if x.shape[2] % self.q_win_size[0] or x.shape[3] % self.q_win_size[1]:
+            # the reference's rearrange 'b d (x w1) (y w2) -> ...' (fax_modules.py:399-401) rejects this
+            raise _einops_error(f"query map {tuple(x.shape[2:])} is not divisible by the window {tuple(self.q_win_size)}")
         xs = ops.nchw_to_nhwc(x, dt)
         f = ops.nchw_to_nhwc(feature.reshape(b * n, c, h, w), dt)
         y = self.plan().run(xs, None, b, f, n, I_inv.reshape(b * n, 3, 3).float().contiguous(),
@@ -393,20 +443,58 @@ class SwapAttention(nn.Module):
         self.register_buffer("relative_position_index", idx)
 
 
-class SwapFusionBlockMask(nn.Module):
+def _mask_u8(mask, B, H, W, L):
+    """(B, H, W, 1, L) reference mask -> (B, H, W, L) uint8 key mask of the attention kernel."""
+    if mask is None or tuple(mask.shape) != (B, H, W, 1, L):
+        # the reference's rearrange 'b (x w1) (y w2) e l -> ...' (swap_fusion_modules.py:172-174) rejects other shapes
+        raise _einops_error(f"mask must be (B, H, W, 1, L) = {(B, H, W, 1, L)}, got {None if mask is None else tuple(mask.shape)}")
+    return (mask[:, :, :, 0, :] != 0).to(torch.uint8).contiguous()
+
+
+class _SwapBlockBase(_Planned):
+    """forward shared by SwapFusionBlockMask / SwapFusionBlock: x (B, L, d, H, W) -> same shape."""
+    _use_mask = False
+
+    def _build_plan(self, dev, dt):
+        return engine.SwapBlockPlan(self, self._use_mask, self.window_size, dev, dt)
+
+    def _run(self, x, mask):
+        _require_inference(self, x)
+        B, L, d, H, W = x.shape
+        ws = self.window_size
+        if H % ws or W % ws:
+            raise _einops_error(f"map {H}x{W} is not divisible by window_size {ws}")      # :175 / Rearrange
+        if L != self.agent_size:
+            raise ValueError(f"agent axis {L} != agent_size {self.agent_size} baked into the bias table")
+        t = ops.nchw_to_nhwc(x.reshape(B * L, d, H, W), self.compute_dtype).reshape(-1, d)
+        mk = _mask_u8(mask, B, H, W, L) if self._use_mask else None
+        y, _ = self.plan().run(t, None, (B, L, H, W, d), mk)
+        return ops.nhwc_to_nchw(y.view(B * L, H, W, d), torch.float32).view(B, L, d, H, W)
+
+
+class SwapFusionBlockMask(_SwapBlockBase):
+    """swap_fusion_modules.py:131-192."""
+    _use_mask = True
+
     def __init__(self, input_dim, mlp_dim, dim_head, window_size, agent_size, drop_out):
         super().__init__()
-        self.window_size = window_size
+        self.window_size, self.agent_size = window_size, agent_size
         mk = lambda: SwapAttention(input_dim, dim_head, drop_out, agent_size, window_size)
         self.window_attention = PreNormResidual(input_dim, mk())
         self.window_ffd = PreNormResidual(input_dim, FeedForward(input_dim, mlp_dim, drop_out))
         self.grid_attention = PreNormResidual(input_dim, mk())
         self.grid_ffd = PreNormResidual(input_dim, FeedForward(input_dim, mlp_dim, drop_out))
 
+    def forward(self, x, mask):
+        return self._run(x, mask)
 
-class SwapFusionBlock(nn.Module):
+
+class SwapFusionBlock(_SwapBlockBase):
+    """swap_fusion_modules.py:195-230 (``forward(x, mask=None)`` ignores the mask, :227-230)."""
+
     def __init__(self, input_dim, mlp_dim, dim_head, window_size, agent_size, drop_out):
         super().__init__()
+        self.window_size, self.agent_size = window_size, agent_size
         mk = lambda: SwapAttention(input_dim, dim_head, drop_out, agent_size, window_size)
         # positions 0,3,4,7 are the reference's parameter-free Rearrange layers
         self.block = nn.Sequential(
@@ -414,6 +502,9 @@ class SwapFusionBlock(nn.Module):
             PreNormResidual(input_dim, FeedForward(input_dim, mlp_dim, drop_out)), nn.Identity(),
             nn.Identity(), PreNormResidual(input_dim, mk()),
             PreNormResidual(input_dim, FeedForward(input_dim, mlp_dim, drop_out)), nn.Identity())
+
+    def forward(self, x, mask=None):
+        return self._run(x, None)
 
 
 class SwapFusionEncoder(_Planned):
@@ -438,7 +529,7 @@ class SwapFusionEncoder(_Planned):
         if L != self.agent_size:
             raise ValueError(f"agent axis {L} != agent_size {self.agent_size} baked into the bias table")
         if H % self.window_size or W % self.window_size:
-            raise ValueError(f"map {H}x{W} is not divisible by window_size {self.window_size}")
+            raise _einops_error(f"map {H}x{W} is not divisible by window_size {self.window_size}")
         return self.plan().run(x, mask_u8)
 
     def forward(self, x, mask=None):
@@ -446,11 +537,7 @@ class SwapFusionEncoder(_Planned):
         _require_inference(self, x)
         B, L, d, H, W = x.shape
         t = ops.nchw_to_nhwc(x.reshape(B * L, d, H, W), self.compute_dtype).view(B, L, H, W, d)
-        mk = None
-        if self.mask:
-            if mask is None or tuple(mask.shape) != (B, H, W, 1, L):
-                raise ValueError("mask=True needs a (B, H, W, 1, L) mask")
-            mk = (mask[:, :, :, 0, :] != 0).to(torch.uint8).contiguous()
+        mk = _mask_u8(mask, B, H, W, L) if self.mask else None
         y = self.run_nhwc(t, mk)
         return ops.nhwc_to_nchw(y, torch.float32)
 
@@ -502,14 +589,59 @@ class BevSegHead(_Planned):
 
 # --------------------------------------------------------------------------- whole models
 class STTF(nn.Module):
+    """corpbevt.py:22-64: affine warp of every agent's BEV map into the ego frame."""
+
     def __init__(self, args):
         super().__init__()
         self.discrete_ratio = args['resolution']
         self.downsample_rate = args['downsample_rate']
+        self.compute_dtype = COMPUTE_DTYPE
+
+    def forward(self, x, spatial_correction_matrix):
+        """x (B, L, C, H, W), spatial_correction_matrix (B, L, 4, 4) -> (B, L, H, W, C)."""
+        _require_inference(self, x)
+        B, L, C, H, W = x.shape
+        t = ops.nchw_to_nhwc(x.reshape(B * L, C, H, W), self.compute_dtype)
+        tm = spatial_correction_matrix.to(device=x.device, dtype=torch.float32).contiguous()
+        full = torch.full((B,), L, dtype=torch.int64, device=x.device)
+        y, _ = ops.sttf_regroup(t, tm, full, B, L, self.discrete_ratio, self.downsample_rate, False)
+        return y.float()
+
+
+class NaiveCompressor(_Planned):
+    """naive_compress.py:5-28 (``compress_raito`` is the reference's spelling)."""
+
+    def __init__(self, input_dim, compress_raito):
+        super().__init__()
+        mid = input_dim // compress_raito
+        self.encoder = nn.Sequential(nn.Conv2d(input_dim, mid, 3, 1, 1), nn.BatchNorm2d(mid, eps=1e-3, momentum=0.01), nn.ReLU())
+        self.decoder = nn.Sequential(nn.Conv2d(mid, input_dim, 3, 1, 1), nn.BatchNorm2d(input_dim, eps=1e-3, momentum=0.01), nn.ReLU(),
+                                     nn.Conv2d(input_dim, input_dim, 3, 1, 1), nn.BatchNorm2d(input_dim, eps=1e-3, momentum=0.01),
+                                     nn.ReLU())
+
+    def _build_plan(self, dev, dt):
+        return engine.CompressorPlan(self, dev, dt)
+
+    def forward(self, x):
+        _require_inference(self, x)
+        return ops.nhwc_to_nchw(self.plan().run(ops.nchw_to_nhwc(x, self.compute_dtype)), torch.float32)
+
+
+def post_process(output_dict):
+    """CameraBevPostprocessor.post_process_train (opv2v/opencood/data_utils/post_processor/
+    camera_bev_postprocessor.py:55-94): per head softmax over classes of seg[:, 0] and its argmax, one kernel."""
+    out = dict(output_dict)
+    for key in ("static", "dynamic"):
+        prob, amap = ops.softmax_argmax_nchw(output_dict[key + "_seg"][:, 0])
+        out[key + "_prob"], out[key + "_map"] = prob, amap
+    return out
 
 
 class CorpBEVT(nn.Module):
-    """corpbevt.py:67-145.  forward(batch_dict) -> {'static_seg','dynamic_seg'} (B,1,classes,H,W)."""
+    """corpbevt.py:67-145.  forward(batch_dict) -> {'static_seg','dynamic_seg'} (B,1,classes,H,W).
+
+    ``write_features`` (default False): also replicate the reference's side effect
+    ``batch_dict['features'] = encoder(x)`` (:113) -- it costs a NHWC->NCHW fp32 copy of every picked level."""
 
     def __init__(self, config):
         super().__init__()
@@ -519,34 +651,53 @@ class CorpBEVT(nn.Module):
         fax_params['backbone_output_shape'] = self.encoder.output_shapes
         self.fax = FAXModule(fax_params)
         if config['compression'] > 0:
-            raise NotImplementedError("NaiveCompressor (compression > 0) is outside the accelerated path")
-        self.compression = False
+            self.compression = True
+            self.naive_compressor = NaiveCompressor(128, config['compression'])
+        else:
+            self.compression = False
         self.downsample_rate = config['sttf']['downsample_rate']
         self.discrete_ratio = config['sttf']['resolution']
         self.use_roi_mask = config['sttf']['use_roi_mask']
         self.sttf = STTF(config['sttf'])
         self.fusion_net = SwapFusionEncoder(config['fax_fusion'])
         if self.fusion_net.mask and not self.use_roi_mask:
-            raise ValueError("mask=True requires use_roi_mask=True (the reference raises an EinopsError here)")
+            # survey quirk Q8: the (B,1,1,1,L) mask cannot be partitioned (swap_fusion_modules.py:172-174)
+            raise _einops_error("mask=True requires use_roi_mask=True")
         self.decoder = NaiveDecoder(config['decoder'])
         self.target = config['target']
         self.seg_head = BevSegHead(self.target, config['seg_head_dim'], config['output_class'])
+        self.write_features = False
 
-    def forward(self, batch_dict):
-        x = batch_dict['inputs']
-        b, l, m = x.shape[:3]
-        feats = self.encoder.features_nhwc(x)
+    def encode_nhwc(self, inputs, intrinsic, extrinsic, batch_dict=None):
+        """encoder -> SinBEVT (-> compressor): (rows, 1, M, H, W, 3) -> (rows, h, w, 128) NHWC 16-bit."""
+        m = inputs.shape[2]
+        feats = self.encoder.features_nhwc(inputs)
         pick = self.encoder.idx_pick
         feats = [feats[i] for i in pick]
-        y = self.fax.run_nhwc(feats, m, batch_dict['intrinsic'], batch_dict['extrinsic'])     # (b*l, H, W, d)
-        record_len = batch_dict['record_len'].to(device=y.device, dtype=torch.int64)
-        tm = batch_dict['transformation_matrix'].to(device=y.device, dtype=torch.float32).contiguous()
+        if self.write_features and batch_dict is not None:
+            b, l = inputs.shape[:2]
+            batch_dict.update({'features': [ops.nhwc_to_nchw(f, torch.float32).view(b, l, m, f.shape[3], f.shape[1], f.shape[2])
+                                            for f in feats]})
+        y = self.fax.run_nhwc(feats, m, intrinsic, extrinsic)                                 # (b*l, H, W, d)
+        if self.compression:
+            y = self.naive_compressor.plan().run(y)
+        return y
+
+    def fuse_nhwc(self, y, tm, record_len):
+        """regroup/STTF/mask -> FuseBEVT -> decoder -> head on device-resident tm (B,L,4,4) fp32, record_len (B) int64."""
         B = record_len.shape[0]
         y, mask = ops.sttf_regroup(y, tm, record_len, B, self.max_cav, self.discrete_ratio, self.downsample_rate,
                                    self.use_roi_mask)
         y = self.fusion_net.run_nhwc(y, mask)                                                # (B, H, W, d)
         y = self.decoder.plan().run(y)
         return self.seg_head.plan().run(y, B, 1)
+
+    def forward(self, batch_dict):
+        x = batch_dict['inputs']
+        y = self.encode_nhwc(x, batch_dict['intrinsic'], batch_dict['extrinsic'], batch_dict)
+        record_len = batch_dict['record_len'].to(device=y.device, dtype=torch.int64)
+        tm = batch_dict['transformation_matrix'].to(device=y.device, dtype=torch.float32).contiguous()
+        return self.fuse_nhwc(y, tm, record_len)
 
 
 class FaxFusedTransformer(nn.Module):

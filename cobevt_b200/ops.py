@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import ConvParams, AttnParams, TokenMap
 
 F16, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_SWISH = 0, 1, 2, 3
 
 
 class _Stats:
@@ -74,7 +74,15 @@ def _ptr(t):
 
 
 def _stream():
+    """Current stream of the CURRENT device; every wrapper is entered with tensors of that device (checked by
+    conv2d_nhwc / window_attention, the two kernels with per-device state)."""
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _same_device(t):
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is {torch.cuda.current_device()}: "
+                           "wrap the call in torch.cuda.device(tensor.device)")
 
 
 def pick_block_n(cout):
@@ -136,6 +144,7 @@ def conv2d_nhwc(x, pc, stride=1, pad=0, act=ACT_NONE, res=None, res32=None, out=
                 in_upsample=False, ln_eps=1e-5, res_rows=0, out_hw=None):
     """x: (N, H, W, Cin) 16-bit contiguous.  Returns (y16 | None, y32 | None, y_ln | None)."""
     assert x.is_cuda and x.is_contiguous() and x.dim() == 4
+    _same_device(x)
     N, H, W, Cin = x.shape
     assert Cin == pc.cin, f"Cin {Cin} != packed {pc.cin}"
     Hl, Wl = (2 * H, 2 * W) if in_upsample else (H, W)
@@ -212,6 +221,7 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     """
     C = heads * 32
     B, qv, Hq, Wq, _ = q.shape
+    _same_device(q)
 
     def tok_stride(t):
         # t may be a last-dim slice of a wider contiguous token tensor
@@ -246,7 +256,14 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     # of the four-warpgroup kernel) + a log-sum-exp merge; e.g. the stage-2 global cross attention, 6 x 420 keys
     per_view = kvmap.w1 * kvmap.w2
     RESIDENT_KEYS = _resident_keys()
-    if (lk > RESIDENT_KEYS and kvmap.views > 1 and per_view <= RESIDENT_KEYS and lq > 2 * 128 and bias is None
+    if (lk > RESIDENT_KEYS and kvmap.views == 1 and not kvmap.grid and (kvmap.w1, kvmap.w2) == (kvmap.H, kvmap.W)
+            and kvmap.H % 2 == 0 and per_view // 2 <= RESIDENT_KEYS and kvmap.Hv == kvmap.H and kvmap.Wv == kvmap.W):
+        # one plane that IS the window (the 1024-token global self-attention, fax_modules.py:132-176): its rows split
+        # into two half-height "views" -- the same memory and the same key order -- so each half is a resident segment
+        # (only the token map changes: pointers and the token stride already describe both halves)
+        kvmap = token_map(2, kvmap.H // 2, kvmap.W, kvmap.H // 2, kvmap.W, False)
+        per_view = kvmap.w1 * kvmap.w2
+    if (lk > RESIDENT_KEYS and kvmap.views > 1 and per_view <= RESIDENT_KEYS and lq > 2 * 128
             and key_mask is None and k_pad is None and kvmap.Hv == kvmap.H and kvmap.Wv == kvmap.W):
         vps = max(1, RESIDENT_KEYS // per_view)                  # views per segment
         while kvmap.views % vps:                                 # equal segments -> ONE launch covers them all
@@ -286,10 +303,24 @@ def pack_rgb8(x, dtype):
     return y
 
 
-def pack_rgb4_padded(x, dtype, pad_top, pad_left, Hp, Wp, nchw=False, mean=None, std=None):
+def pack_rgb4_padded(x, dtype, pad_top, pad_left, Hp, Wp, nchw=False, mean=None, std=None, bgr=False):
     """x (N, H, W, 3) [or (N, 3, H, W) with nchw=True] fp32 -> (N, Hp, Wp, 4) 16-bit, zero border;
-    optional per-channel (x - mean) / std (host triples)."""
-    assert x.dtype == torch.float32 and x.is_contiguous()
+    optional per-channel (x - mean) / std (host triples).  uint8 (N, H, W, 3) frames: ((x / 255) - mean) / std
+    with an optional BGR -> RGB swap (rgb_preprocessor.py:16-46)."""
+    assert x.is_contiguous()
+    if x.dtype == torch.uint8:
+        assert not nchw and x.shape[-1] == 3
+        N, H, W, _ = x.shape
+        y = torch.empty(N, Hp, Wp, 4, dtype=dtype, device=x.device)
+        m3 = s3 = None
+        if mean is not None:
+            m3 = (ctypes.c_float * 3)(*[float(v) for v in mean])
+            s3 = (ctypes.c_float * 3)(*[float(v) for v in std])
+        with _timed("eltwise", 0, "stage_rgb_u8"):
+            _lib.check(_lib.lib().cobevt_stage_rgb_u8(_ptr(x), _ptr(y), N, H, W, Hp, Wp, pad_top, pad_left, 1 if bgr else 0,
+                                                      m3, s3, dtype_code(dtype), _stream()), "cobevt_stage_rgb_u8")
+        return y
+    assert x.dtype == torch.float32 and not bgr
     if nchw:
         N, _, H, W = x.shape
         assert x.shape[1] == 3
@@ -442,3 +473,58 @@ def nhwc_to_nchw(x, dtype, c=None):
         _lib.check(_lib.lib().cobevt_permute(_ptr(x), _ptr(y), N, C, H, W, cp, 0, _any_code(x.dtype), _any_code(dtype), _stream()),
                    "cobevt_permute")
     return y
+
+
+def softmax_argmax_nchw(seg):
+    """seg (N, C, H, W) fp32 -> (softmax over C (N, C, H, W) fp32, argmax (N, H, W) int64)."""
+    seg = seg.float().contiguous()
+    N, C, H, W = seg.shape
+    prob = torch.empty_like(seg)
+    amap = torch.empty(N, H, W, dtype=torch.int64, device=seg.device)
+    with _timed("eltwise", 0, "softmax_argmax"):
+        _lib.check(_lib.lib().cobevt_softmax_argmax(_ptr(seg), _ptr(prob), _ptr(amap), N, C, H * W, _stream()),
+                   "cobevt_softmax_argmax")
+    return prob, amap
+
+
+def resize_nearest(x, scale):
+    """F.interpolate(x, scale_factor=scale, recompute_scale_factor=False) (default 'nearest') on NHWC 16-bit."""
+    import math
+    N, H, W, C = x.shape
+    OH, OW = int(math.floor(H * scale)), int(math.floor(W * scale))
+    y = torch.empty(N, OH, OW, C, dtype=x.dtype, device=x.device)
+    inv = 1.0 / scale
+    with _timed("eltwise", 0, "resize_nearest"):
+        _lib.check(_lib.lib().cobevt_resize_nearest(_ptr(x), _ptr(y), N, H, W, C, OH, OW, inv, inv, _stream()),
+                   "cobevt_resize_nearest")
+    return y
+
+
+def dwconv_swish(x, w, bias, K, stride, pad_top, pad_left, OH, OW, sums=None):
+    """x (N,H,W,C) 16-bit; w (K,K,C), bias (C) fp32 (BatchNorm folded) -> swish(dwconv) (N,OH,OW,C); sums (N,C) fp32
+    accumulates the per-channel output sums (squeeze)."""
+    N, H, W, C = x.shape
+    y = torch.empty(N, OH, OW, C, dtype=x.dtype, device=x.device)
+    with _timed("eltwise", 2 * N * OH * OW * C * K * K, f"dwconv_swish k{K} s{stride} C={C} {H}x{W}"):
+        _lib.check(_lib.lib().cobevt_dwconv_swish(_ptr(x), _f32(w), _f32(bias), _ptr(y), _ptr(sums), N, H, W, C, K, stride,
+                                                  pad_top, pad_left, OH, OW, dtype_code(x.dtype), _stream()),
+                   "cobevt_dwconv_swish")
+    return y
+
+
+def se_gate(sums, hw, w1, b1, w2, b2):
+    N, C = sums.shape
+    gate = torch.empty_like(sums)
+    with _timed("eltwise", 0, "se_gate"):
+        _lib.check(_lib.lib().cobevt_se_gate(_f32(sums), 1.0 / hw, _f32(w1), _f32(b1), _f32(w2), _f32(b2), _ptr(gate), N, C,
+                                             w1.shape[0], _stream()), "cobevt_se_gate")
+    return gate
+
+
+def scale_channels_(x, gate):
+    """x (N,H,W,C) 16-bit *= gate (N,C) fp32, in place."""
+    N, H, W, C = x.shape
+    with _timed("eltwise", 0, "scale_channels"):
+        _lib.check(_lib.lib().cobevt_scale_channels(_ptr(x), _f32(gate), _ptr(x), N, H * W, C, dtype_code(x.dtype), _stream()),
+                   "cobevt_scale_channels")
+    return x

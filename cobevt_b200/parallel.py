@@ -5,7 +5,8 @@ are split contiguously over ranks.  FuseBEVT is the only place agents of one sam
 each rank all-gathers the per-agent BEV tiles (rows x 32 x 32 x 128 16-bit, <= 256 KiB/row --
 latency-bound, so a plain NCCL all-gather on the compute stream) and then runs
 regroup/STTF -> FuseBEVT -> decoder -> head for the contiguous block of samples it owns.
-When no sample straddles a rank boundary the exchange is skipped entirely.
+When no sample straddles a rank boundary the exchange is skipped entirely.  ShardedCorpBEVT captures
+encode + all-gather + fuse into a single CUDA graph.
 
 The compute steps are injected (``encode`` / ``fuse``) so the same plumbing is exercised by
 the world_size-2 gloo tests on CPU with the oracle's math standing in for the kernels.
@@ -74,25 +75,35 @@ def sharded_forward(encode, fuse, local_inputs, record_len, rank, world, group=N
 class _Graphed:
     """Replays a fixed-shape kernel sequence as one CUDA graph (launch-latency removal only: the
     captured work is exactly the eager kernel sequence).  Inputs are bound at capture time; later
-    calls copy into those buffers when handed different tensors."""
+    calls copy into those buffers when handed different tensors (same shape / dtype / device -- anything
+    else raises).  The returned tensors are the graph's static output buffers: they are overwritten by
+    the next call, clone them to keep a result."""
 
-    def __init__(self, fn):
+    def __init__(self, fn, capture_error_mode="global"):
         self.fn, self.graph, self.static_in, self.static_out = fn, None, None, None
+        self.capture_error_mode = capture_error_mode
 
     def __call__(self, *tensors):
         if self.graph is None:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up outside capture: plans, smem attributes
+            with torch.cuda.stream(side):          # warm-up outside capture: plans, smem attributes, NCCL channels
                 for _ in range(2):
                     self.fn(*tensors)
             torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
             self.static_in = tensors
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, capture_error_mode=self.capture_error_mode):
                 self.static_out = self.fn(*self.static_in)
         else:
-            for dst, src in zip(self.static_in, tensors):
+            if len(tensors) != len(self.static_in):
+                raise ValueError(f"graph was captured with {len(self.static_in)} inputs, got {len(tensors)}")
+            for i, (dst, src) in enumerate(zip(self.static_in, tensors)):
+                if (dst.shape, dst.dtype, dst.device) != (src.shape, src.dtype, src.device):
+                    raise ValueError(f"input {i}: graph captured for {tuple(dst.shape)} {dst.dtype} {dst.device}, "
+                                     f"got {tuple(src.shape)} {src.dtype} {src.device}; build a new ShardedCorpBEVT "
+                                     "for a different batch shape")
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src, non_blocking=True)
         self.graph.replay()
@@ -100,55 +111,89 @@ class _Graphed:
 
 
 class ShardedCorpBEVT:
-    """CorpBEVT (modules.py) run agent-row-sharded over a process group.  With ``graphs=True`` the
-    encode (encoder + SinBEVT) and fuse (STTF + FuseBEVT + decoder + head) kernel sequences are each
-    captured once into a CUDA graph; the NCCL all-gather between them stays an eager call."""
+    """CorpBEVT (modules.py) run agent-row-sharded over a process group.
 
-    def __init__(self, model, rank=0, world=1, group=None, graphs=False):
+    graphs=False   every kernel launched eagerly.
+    graphs=True    the whole step -- encode (encoder + SinBEVT), the NCCL all-gather of the per-agent BEV
+                   tiles when a sample straddles ranks, and fuse (STTF + FuseBEVT + decoder + head) -- is
+                   captured once into ONE CUDA graph (``single_graph``; NCCL collectives are capturable), so
+                   no host work or graph break sits between the SinBEVT epilogue and the gather.  If the
+                   capture of the collective is refused by the runtime the step falls back to two graphs with
+                   an eager all-gather in between (``self.mode`` says which ran).
+    The agent->ego transforms and record_len are tiny host-side values: they are re-staged into static device
+    buffers on EVERY call (never cached by address), so in-place updates and recycled allocations are safe."""
+
+    def __init__(self, model, rank=0, world=1, group=None, graphs=False, single_graph=True):
         self.m, self.rank, self.world, self.group = model, rank, world, group
-        self.graphs = graphs
-        self._g_encode = self._g_fuse = None
-        self._fuse_key = None
+        self.graphs, self.single_graph = graphs, single_graph
+        self.mode = "eager" if not graphs else None
+        self._g_step = self._g_encode = self._g_fuse = None
+        self._layout = None
+        self._rl = self._tm = None
+
+    # ---- the two kernel sequences --------------------------------------------------------------------
+    def _encode_k(self, inputs, intrinsic, extrinsic):
+        return self.m.encode_nhwc(inputs, intrinsic, extrinsic)
+
+    def _fuse_k(self, tiles, tm, rl):
+        return self.m.fuse_nhwc(tiles, tm, rl)
+
+    def _stage_layout(self, record_len, transformation_matrix, s0, s1, dev):
+        """host -> static device buffers; a changed layout (different record_len slice) drops the fuse graphs."""
+        key = tuple(record_len[s0:s1])
+        if self._layout != key:
+            self._layout = key
+            self._rl = torch.tensor(list(key), dtype=torch.int64, device=dev)
+            self._tm = torch.empty((s1 - s0, self.m.max_cav, 4, 4), dtype=torch.float32, device=dev)
+            self._g_fuse = self._g_step = None
+        self._tm.copy_(transformation_matrix[s0:s1].to(dtype=torch.float32), non_blocking=True)
 
     def __call__(self, local_batch, record_len, transformation_matrix):
         """local_batch: this rank's rows of inputs/intrinsic/extrinsic; record_len: global
         python list; transformation_matrix: global (B, max_cav, 4, 4) tensor (replicated)."""
-        from . import ops
-        m = self.m
-        n_cams = local_batch['inputs'].shape[2]
+        dev = local_batch['inputs'].device
+        s0, s1 = sample_shard(len(record_len), self.world, self.rank)
+        if s1 > s0:
+            self._stage_layout(record_len, transformation_matrix, s0, s1, dev)
+        lb = local_batch
 
-        def encode_k(inputs, intrinsic, extrinsic):
-            feats = m.encoder.features_nhwc(inputs)
-            feats = [feats[i] for i in m.encoder.idx_pick]
-            return m.fax.run_nhwc(feats, n_cams, intrinsic, extrinsic)
+        if self.graphs and self.single_graph and self.mode in (None, "single-graph") and s1 > s0:
+            def step_k(inputs, intrinsic, extrinsic, tm, rl):
+                return sharded_forward(lambda _: self._encode_k(inputs, intrinsic, extrinsic),
+                                       lambda tiles, a, b: self._fuse_k(tiles.contiguous(), tm, rl),
+                                       None, record_len, self.rank, self.world, self.group)
+            if self._g_step is None:
+                try:
+                    g = _Graphed(step_k, capture_error_mode="thread_local")
+                    out = g(lb['inputs'], lb['intrinsic'], lb['extrinsic'], self._tm, self._rl)
+                    self._g_step, self.mode = g, "single-graph"
+                    return out
+                except Exception as e:           # capture of the collective refused: two graphs + eager gather
+                    if self.world == 1:
+                        raise
+                    self.mode = "two-graphs"
+                    self.capture_error = repr(e)[:300]
+                    torch.cuda.synchronize()
+            else:
+                return self._g_step(lb['inputs'], lb['intrinsic'], lb['extrinsic'], self._tm, self._rl)
+        if self.graphs and self.mode is None:
+            self.mode = "two-graphs"
 
-        def fuse_k(tiles, tm, rl):
-            B = rl.shape[0]
-            y, mask = ops.sttf_regroup(tiles, tm, rl, B, m.max_cav, m.discrete_ratio, m.downsample_rate, m.use_roi_mask)
-            y = m.fusion_net.run_nhwc(y, mask)
-            y = m.decoder.plan().run(y)
-            return m.seg_head.plan().run(y, B, 1)
-
-        def encode(lb):
+        def encode(_):
             if not self.graphs:
-                return encode_k(lb['inputs'], lb['intrinsic'], lb['extrinsic'])
+                return self._encode_k(lb['inputs'], lb['intrinsic'], lb['extrinsic'])
             if self._g_encode is None:
-                self._g_encode = _Graphed(encode_k)
+                self._g_encode = _Graphed(self._encode_k)
             return self._g_encode(lb['inputs'], lb['intrinsic'], lb['extrinsic'])
 
-        def fuse(tiles, s0, s1):
-            if s1 <= s0:
+        def fuse(tiles, a, b):
+            if b <= a:
                 return None
-            dev = tiles.device
-            key = (tuple(record_len[s0:s1]), transformation_matrix.data_ptr())
-            if self._fuse_key != key:       # host -> device staging of the tiny per-layout tensors, once
-                self._fuse_key = key
-                self._rl = torch.tensor(record_len[s0:s1], dtype=torch.int64, device=dev)
-                self._tm = transformation_matrix[s0:s1].to(device=dev, dtype=torch.float32).contiguous()
-                self._g_fuse = _Graphed(fuse_k) if self.graphs else None
             tiles = tiles.contiguous()
+            if not self.graphs:
+                return self._fuse_k(tiles, self._tm, self._rl)
             if self._g_fuse is None:
-                return fuse_k(tiles, self._tm, self._rl)
+                self._g_fuse = _Graphed(self._fuse_k)
             return self._g_fuse(tiles, self._tm, self._rl)
 
-        return sharded_forward(encode, fuse, local_batch, record_len, self.rank, self.world, self.group)
+        return sharded_forward(encode, fuse, None, record_len, self.rank, self.world, self.group)

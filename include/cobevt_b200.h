@@ -29,7 +29,7 @@ extern "C" {
 #define COBEVT_ERR_CUDA (-3)
 
 enum { COBEVT_F16 = 0, COBEVT_BF16 = 1 };
-enum { COBEVT_ACT_NONE = 0, COBEVT_ACT_RELU = 1, COBEVT_ACT_GELU = 2 };
+enum { COBEVT_ACT_NONE = 0, COBEVT_ACT_RELU = 1, COBEVT_ACT_GELU = 2, COBEVT_ACT_SWISH = 3 };
 
 int cobevt_version(void);
 const char* cobevt_last_error(void);
@@ -102,7 +102,8 @@ typedef struct {
   void* out;          /* q_mean ? (B, q.Hv, q.Wv, C) : (B, q.views, q.Hv, q.Wv, C)   */
   const void* k_pad;  /* [C] 16-bit token used for padded key positions, or NULL     */
   const void* v_pad;
-  const float* bias;  /* (heads, Lq, Lk) fp32 additive bias or NULL                  */
+  const float* bias;  /* (heads, Lq, Lk) fp32 additive bias or NULL; Lk counts the keys of ALL kv_views_total
+                         views of the window (a key-segment call adds its own slice of every row)     */
   const uint8_t* key_mask; /* (B, kv.Hv, kv.Wv, kv.views) 1 = keep, 0 = -inf; or NULL */
   CobevtTokenMap qmap, kvmap;
   int32_t B, heads;
@@ -190,6 +191,34 @@ int cobevt_sttf_regroup(const void* x, const float* tm, const int64_t* record_le
                         uint8_t* mask, int32_t B, int32_t L, int32_t H, int32_t W, int32_t C,
                         float discrete_ratio, float downsample_rate, int32_t use_roi_mask,
                         int32_t dtype, void* stream);
+/* uint8 camera frames (N,H,W,3) -> (N,Hp,Wp,4) 16-bit RGBx with a zero border, fusing the RgbPreProcessor
+ * arithmetic of opv2v/opencood/data_utils/pre_processor/rgb_preprocessor.py:16-36 (optional BGR->RGB :38-46,
+ * x/255 :33-34, (x-mean)/std :24-31) into the stem's input staging.  mean3/std3: HOST pointers
+ * (3 floats) or NULL. */
+int cobevt_stage_rgb_u8(const uint8_t* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
+                        int32_t pad_top, int32_t pad_left, int32_t bgr, const float* mean3_host,
+                        const float* std3_host, int32_t dtype, void* stream);
+/* prob = softmax(seg, dim=1), amap = argmax(prob, dim=1) for seg (N,C,HW) fp32 NCHW: softmax_argmax of
+ * opv2v/opencood/data_utils/post_processor/camera_bev_postprocessor.py:55-59 (used by post_process_train :61-87) */
+int cobevt_softmax_argmax(const float* seg, float* prob, int64_t* amap, int32_t N, int32_t C, int64_t HW, void* stream);
+/* F.interpolate(x, scale_factor=s, recompute_scale_factor=False) in its default 'nearest' mode on NHWC 16-bit
+ * (nuscenes .../encoder_pyramid_axial.py:492-493): src index = min(floor(dst * src_per_dst), in - 1) */
+int cobevt_resize_nearest(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
+                          float src_per_dst_h, float src_per_dst_w, void* stream);
+/* ---- MBConv pieces of the EfficientNet-B4 prefix (nuscenes .../backbones/efficientnet.py:56-69; arithmetic =
+ * efficientnet_pytorch 0.7.1 MBConvBlock, package absent from the reference tree: parity unpinned) ------------- */
+/* y = swish(depthwise KxK conv(x; w) + bias): NHWC 16-bit, w (K,K,C) fp32 with BN folded, asymmetric "static same"
+ * padding (pad_top/pad_left before, the rest implied by OH/OW); sums (N,C) fp32 or NULL: += sum over pixels of y
+ * (the squeeze of squeeze-excite; caller zeroes it) */
+int cobevt_dwconv_swish(const void* x, const float* w, const float* bias, void* y, float* sums, int32_t N, int32_t H,
+                        int32_t W, int32_t C, int32_t K, int32_t stride, int32_t pad_top, int32_t pad_left, int32_t OH,
+                        int32_t OW, int32_t dtype, void* stream);
+/* gate (N,C) = sigmoid(W2 swish(W1 (sums * inv_hw) + b1) + b2); w1 (Cse,C), w2 (C,Cse) fp32 */
+int cobevt_se_gate(const float* sums, float inv_hw, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float* gate, int32_t N, int32_t C, int32_t Cse, void* stream);
+/* y[n,p,c] = x[n,p,c] * gate[n,c] (in place allowed) */
+int cobevt_scale_channels(const void* x, const float* gate, void* y, int32_t N, int64_t HW, int32_t C, int32_t dtype,
+                          void* stream);
 /* NCHW <-> NHWC(Cpad) with dtype conversion; module API boundaries only */
 int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                    int32_t to_nhwc, int32_t src_dtype, int32_t dst_dtype, void* stream);

@@ -457,9 +457,9 @@ def naive_decoder(x, sd, prefix, num_layer):
 def bev_seg_head(x, sd, prefix, target, b, l):
     """M/sub_modules/bev_seg_head.py:35-61."""
     out = {}
-    if target in ("dynamic", "both"):
+    if target != "static":         # 'dynamic' and every other target string run the dynamic head (:36-39,50-53)
         out["dynamic_seg"] = _conv(x, sd, prefix + "dynamic_head", 1, 1).reshape(b, l, -1, *x.shape[2:])
-    if target in ("static", "both"):
+    if target != "dynamic":
         out["static_seg"] = _conv(x, sd, prefix + "static_head", 1, 1).reshape(b, l, -1, *x.shape[2:])
     if target == "dynamic":
         out["static_seg"] = torch.zeros_like(out["dynamic_seg"])
@@ -468,14 +468,36 @@ def bev_seg_head(x, sd, prefix, target, b, l):
     return out
 
 
+def naive_compressor(x, sd, prefix):
+    """NaiveCompressor.forward, M/sub_modules/naive_compress.py:5-28: conv3x3-BN-ReLU down to C/ratio, then two
+    conv3x3-BN-ReLU back up; every BatchNorm has eps = 1e-3 (:11,17,20)."""
+    y = F.relu(_bn(_conv(x, sd, prefix + "encoder.0", 1, 1), sd, prefix + "encoder.1", eps=1e-3))
+    y = F.relu(_bn(_conv(y, sd, prefix + "decoder.0", 1, 1), sd, prefix + "decoder.1", eps=1e-3))
+    return F.relu(_bn(_conv(y, sd, prefix + "decoder.3", 1, 1), sd, prefix + "decoder.4", eps=1e-3))
+
+
+def post_process(output_dict):
+    """CameraBevPostprocessor.post_process_train, opv2v/opencood/data_utils/post_processor/
+    camera_bev_postprocessor.py:55-94: per head softmax over the class axis of seg[:, 0] and its argmax."""
+    out = dict(output_dict)
+    for key in ("static", "dynamic"):
+        seg = output_dict[key + "_seg"][:, 0]
+        prob = torch.softmax(seg, dim=1)
+        out[key + "_prob"] = prob
+        out[key + "_map"] = torch.argmax(prob, dim=1)
+    return out
+
+
 # --------------------------------------------------------------------------- whole models
 def corpbevt(batch, sd, cfg):
-    """CorpBEVT.forward, M/corpbevt.py:104-145 (compression == 0)."""
+    """CorpBEVT.forward, M/corpbevt.py:104-145."""
     x = batch["inputs"]
     enc = cfg["encoder"]
     feats = resnet_encoder(x, sd, "encoder.", enc["num_layers"], enc["id_pick"])
     y = fax_module(feats, batch["intrinsic"], batch["extrinsic"], sd, "fax.", cfg["fax"])
     y = y.squeeze(1)
+    if cfg.get("compression", 0) > 0:                                            # :118-121
+        y = naive_compressor(y, sd, "naive_compressor.")
     y, mask = regroup(y, batch["record_len"].tolist(), cfg["max_cav"])
     st = cfg["sttf"]
     tm = batch["transformation_matrix"]
@@ -572,3 +594,73 @@ def cross_view_transformer(batch, sd, cfg, backbone_fn):
     z = F.relu(_bn(_conv(y, sd, "to_logits.0", 1, 1), sd, "to_logits.1"))
     z = _conv(z, sd, "to_logits.3")
     return {k: z[:, a:b_] for k, (a, b_) in cfg["outputs"].items()}
+
+
+# --------------------------------------------------------------------------- EfficientNet-B4 prefix (nuScenes backbone)
+# PARITY UNPINNED: the arithmetic lives in the third-party package efficientnet_pytorch==0.7.1
+# (nuscenes/requirements.txt:13), which is neither vendored under /root/reference nor installed.  What follows
+# restates that package's published MBConvBlock / Conv2dStaticSamePadding semantics for exactly the layers the
+# reference runs (nuscenes/cross_view_transformer/model/backbones/efficientnet.py:56-69: stem + blocks 0..10), and
+# is pinned STRUCTURALLY by strict-loading the 236 backbone tensors of the shipped checkpoint
+# (tests/test_effnet_cpu.py); its numbers cannot be checked against the package here.
+
+# (kernel, stride, expand_ratio, in, out) of MBConv blocks 0..10 of EfficientNet-B4 (width 1.4, depth 1.8,
+# divisor 8), grouped as efficientnet.py:15-20 slices them: (0,3), (3,7), (7,11)
+EFFNET_B4_PREFIX = (
+    ((3, 1, 1, 48, 24), (3, 1, 1, 24, 24), (3, 2, 6, 24, 32)),
+    ((3, 1, 6, 32, 32), (3, 1, 6, 32, 32), (3, 1, 6, 32, 32), (5, 2, 6, 32, 56)),
+    ((5, 1, 6, 56, 56), (5, 1, 6, 56, 56), (5, 1, 6, 56, 56), (3, 2, 6, 56, 112)),
+)
+EFFNET_BN_EPS = 1e-3
+EFFNET_B4_IMAGE_SIZE = 380        # Conv2dStaticSamePadding pads for the model's NOMINAL resolution, not the input's
+
+
+def static_same_pad(size, k, s):
+    """(before, after) zero padding of efficientnet_pytorch's Conv2dStaticSamePadding for nominal extent `size`."""
+    out = -(-size // s)
+    pad = max((out - 1) * s + k - size, 0)
+    return pad // 2, pad - pad // 2
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def _conv_static_same(x, w, stride, nominal):
+    k = w.shape[-1]
+    b, a = static_same_pad(nominal, k, stride)
+    return F.conv2d(F.pad(x, (b, a, b, a)), w, None, stride=stride, groups=w.shape[0] if w.shape[1] == 1 else 1)
+
+
+def mbconv_block(x, sd, p, k, stride, expand, cin, cout, nominal):
+    """MBConvBlock.forward (eval: no drop-connect): expand 1x1-BN-swish, depthwise kxk-BN-swish, squeeze-excite
+    (avg-pool -> 1x1 -> swish -> 1x1 -> sigmoid gate), project 1x1-BN, identity skip when stride 1 and cin == cout."""
+    y = x
+    if expand != 1:
+        y = _swish(_bn(F.conv2d(y, sd[p + "._expand_conv.weight"]), sd, p + "._bn0", EFFNET_BN_EPS))
+    y = _swish(_bn(_conv_static_same(y, sd[p + "._depthwise_conv.weight"], stride, nominal), sd, p + "._bn1", EFFNET_BN_EPS))
+    sq = y.mean((2, 3), keepdim=True)
+    sq = F.conv2d(_swish(F.conv2d(sq, sd[p + "._se_reduce.weight"], sd[p + "._se_reduce.bias"])),
+                  sd[p + "._se_expand.weight"], sd[p + "._se_expand.bias"])
+    y = torch.sigmoid(sq) * y
+    y = _bn(F.conv2d(y, sd[p + "._project_conv.weight"]), sd, p + "._bn2", EFFNET_BN_EPS)
+    if stride == 1 and cin == cout:
+        y = y + x
+    return y
+
+
+def efficientnet_b4_prefix(image_nchw, sd, prefix):
+    """EfficientNetExtractor.forward (efficientnet.py:80-94) for layer_names reduction_2..4: stem + MBConv groups
+    (0,3), (3,7), (7,11); returns the three group outputs (32 / 56 / 112 channels at strides 4 / 8 / 16).
+    Parameters: `prefix`layers.0.{0,1} (stem conv, BN), `prefix`layers.{1,2,3}.{j}._* (blocks)."""
+    nominal = EFFNET_B4_IMAGE_SIZE
+    x = _swish(_bn(_conv_static_same(image_nchw, sd[prefix + "layers.0.0.weight"], 2, nominal), sd, prefix + "layers.0.1",
+                   EFFNET_BN_EPS))
+    nominal = -(-nominal // 2)
+    feats = []
+    for gi, group in enumerate(EFFNET_B4_PREFIX):
+        for j, (k, s, e, cin, cout) in enumerate(group):
+            x = mbconv_block(x, sd, f"{prefix}layers.{gi + 1}.{j}", k, s, e, cin, cout, nominal)
+            nominal = -(-nominal // s)
+        feats.append(x)
+    return feats

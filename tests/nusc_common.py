@@ -48,3 +48,44 @@ def oracle_forward(batch, sd, cfg):
     from oracle import cobevt_oracle as orc
     backbone = lambda img: orc.resnet_levels(img, sd, "encoder.backbone.trunk.", 34, 3)
     return orc.cross_view_transformer(batch, sd, cfg, backbone)
+
+
+class FakeEffNetFeatures(nn.Module):
+    """Shape-compatible, deterministic stand-in for the EfficientNet-B4 prefix (32/56/112 channels at strides
+    4/8/16) behind the ``backbone=`` injection point: real-weight parity of everything after the backbone on
+    boxes where ``efficientnet_pytorch`` is absent."""
+
+    def __init__(self, H, W):
+        super().__init__()
+        self.output_shapes = [torch.Size((1, c, H // s, W // s)) for c, s in ((32, 4), (56, 8), (112, 16))]
+
+    def forward(self, x):
+        g = torch.Generator().manual_seed(7)
+        return [torch.randn(x.shape[0], *s[1:], generator=g).to(x.device) for s in self.output_shapes]
+
+
+def load_shipped_ckpt(path="/root/reference/nuscenes/logs/sinbevt_nuscenes_vehicle_50k.ckpt"):
+    """state_dict of the Lightning checkpoint shipped with the reference: omegaconf /
+    lightning classes inside the pickle are replaced by permissive stubs."""
+    import pickle
+    import types
+
+    class _Stub:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, st):
+            self.__dict__.update(st if isinstance(st, dict) else {})
+
+    class _U(pickle.Unpickler):
+        def find_class(self, mod, name):
+            try:
+                return super().find_class(mod, name)
+            except Exception:
+                return type(name, (_Stub,), {})
+
+    pm = types.ModuleType("stub_pickle")
+    pm.Unpickler = _U
+    pm.load = lambda f, **kw: _U(f).load()
+    pm.__name__ = "pickle"
+    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=pm)["state_dict"]

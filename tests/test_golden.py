@@ -34,12 +34,33 @@ def _load_cvt(fx):
     return fx, cfg, model, sd, batch
 
 
+def _load_cvt_real(fx):
+    """Trained non-backbone weights of the shipped checkpoint (stored in the fixture, matrices in fp16) behind a
+    deterministic stand-in for the EfficientNet features."""
+    import nusc_common as nc
+    from cobevt_b200 import synth, nuscenes as ns
+    cfg = fx["config"]
+    e = copy.deepcopy(cfg['encoder'])
+    enc = ns.PyramidAxialEncoder(nc.FakeEffNetFeatures(fx["H"], fx["W"]), e['cross_view'], e['cross_view_swap'],
+                                 e['bev_embedding'], e['self_attn'], e['dim'], e['middle'], e['scale'])
+    model = ns.CrossViewTransformer(enc, ns.Decoder(cfg['decoder_dim'], cfg['decoder_blocks'], True, 2), cfg['dim_last'],
+                                    copy.deepcopy(cfg['outputs'])).eval()
+    w = {k: v.float() if v.is_floating_point() else v for k, v in fx["weights"].items()}
+    missing, unexpected = model.load_state_dict(w, strict=False)
+    assert not unexpected and not missing, (missing[:3], unexpected[:3])
+    sd = {k: v.float() for k, v in model.state_dict().items()}
+    batch = synth.synth_nuscenes_batch(fx["H"], fx["W"], b=1, n_cams=fx["n_cams"], seed=fx["input_seed"])
+    return fx, cfg, model, sd, batch
+
+
 def _load(path):
     import cobevt_b200 as cb
     from cobevt_b200 import synth
     fx = torch.load(path, weights_only=False)
     if fx["kind"] == "cvt":
         return _load_cvt(fx)
+    if fx["kind"] == "cvt_real":
+        return _load_cvt_real(fx)
     cfg = fx["config"]
     cls = cb.CorpBEVT if fx["kind"] == "corpbevt" else cb.FaxFusedTransformer
     model = cls(copy.deepcopy(cfg)).eval()
@@ -62,13 +83,18 @@ def test_fixtures_present():
 def test_oracle_reproduces_reference_output(path):
     from oracle import cobevt_oracle as orc
     fx, cfg, _, sd, batch = _load(path)
-    if fx["kind"] == "cvt":
+    if fx["kind"] in ("cvt", "cvt_real"):
         import nusc_common as nc
         with torch.no_grad():
-            got = nc.oracle_forward(batch, sd, cfg)
+            if fx["kind"] == "cvt":
+                got = nc.oracle_forward(batch, sd, cfg)
+            else:
+                got = orc.cross_view_transformer(batch, sd, cfg, lambda img: nc.FakeEffNetFeatures(fx["H"], fx["W"])(img))
+        # trained weights: fp32 re-association noise reaches 1.3e-5 (see tests/test_nuscenes_cpu.py)
+        tol = 5e-5 if fx["kind"] == "cvt_real" else 1e-5
         for k, want in fx["outputs"].items():
             assert got[k].shape == want.shape
-            assert rel(got[k], want) < 1e-5, k
+            assert rel(got[k], want) < tol, k
         return
     fn = orc.corpbevt if fx["kind"] == "corpbevt" else orc.fax_fused_transformer
     with torch.no_grad():
@@ -77,23 +103,52 @@ def test_oracle_reproduces_reference_output(path):
     assert rel(got, fx["dynamic_seg"]) < 1e-5
 
 
+def _record(case, key, err, dtype="f16"):
+    """measured parity errors land in gpurun_out/parity_r2.jsonl (scratch) so a round can re-derive the bounds"""
+    import json
+    d = os.path.join(os.path.dirname(HERE), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_r2.jsonl"), "a") as f:
+            f.write(json.dumps({"case": case, "key": key, "dtype": dtype, "rel_err": err}) + "\n")
+
+
+# Whole-model tolerance (max|d| / max|ref|, the CUDA path in 16-bit storage vs the fp32 reference golden).
+# The north_star's "1e-3 rel fp16" holds per kernel (tests/test_kernels_gpu.py) but not through ~100 chained
+# 16-bit GEMMs: the UNMODIFIED reference run under torch.autocast(float16) moves 2.3e-3 .. 5.9e-3 away from its own
+# fp32 output on these very fixtures (tests/golden/autocast_error.json, made by make_golden.py --autocast), bf16
+# 1.4e-2 .. 4.3e-2.  The bounds below are this repo's MEASURED errors on B200 x 1.5 (profiles/r02_parity.json),
+# all at or below the reference's own 16-bit deviation.
+FP16_BOUND = {
+    "default": 4.5e-3,                       # measured 1.9e-3 .. 2.9e-3 (reference under fp16 autocast: 2.3e-3 .. 5.4e-3)
+    # nuScenes 'center' head: measured 4.9e-3 .. 5.3e-3 (reference autocast 6.6e-3 .. 7.4e-3)
+    "cvt_c2_bev256_2cam": 8e-3, "cvt_c2_bev256_6cam": 8e-3, "cvt_native200_1cam": 8e-3,
+    # trained weights on out-of-distribution stand-in features amplify 16-bit rounding: the reference's own fp16
+    # autocast run is 4.8e-2 / 4.9e-2 away from its fp32 output here; measured 2.1e-2
+    "cvt_realweights_6cam": 3.3e-2,
+}
+BF16_BOUND = 6.5e-2                          # measured 1.8e-2 .. 4.2e-2 (reference bf16 autocast 1.4e-2 .. 4.4e-2)
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-3] for p in FIXTURES])
-def test_cuda_path_matches_reference_output(path):
+def test_cuda_path_matches_reference_output(path, dtype):
+    import cobevt_b200 as cb
     from cobevt_b200 import synth
     fx, cfg, model, sd, batch = _load(path)
-    if fx["kind"] == "cvt":
-        with torch.no_grad():
-            got = model.cuda()(synth.to_device(batch, "cuda"))
-        torch.cuda.synchronize()
-        for k, want in fx["outputs"].items():
-            e = rel(got[k], want)
-            print(fx["case"], k, "rel err vs reference golden", e)
-            assert e < 1e-2, (k, e)
-        return
+    if dtype == "bf16":
+        if fx["case"] not in ("corpbevt_small_ragged", "corpbevt_northstar_1agent", "cvt_c2_bev256_6cam"):
+            pytest.skip("bf16 models are checked on three representative fixtures")
+        cb.set_compute_dtype(model, torch.bfloat16)
+    bound = BF16_BOUND if dtype == "bf16" else FP16_BOUND.get(fx["case"], FP16_BOUND["default"])
     with torch.no_grad():
-        got = model.cuda()(synth.to_device(batch, "cuda"))["dynamic_seg"]
+        got = model.cuda()(synth.to_device(batch, "cuda"))
     torch.cuda.synchronize()
-    e = rel(got, fx["dynamic_seg"])
-    print(fx["case"], "rel err vs reference golden", e)
-    assert e < 1e-2, e     # fp16 storage through ~60 chained kernels; single ops are held to 2e-3
+    wants = fx["outputs"] if fx["kind"] in ("cvt", "cvt_real") else {"dynamic_seg": fx["dynamic_seg"]}
+    errs = {}
+    for k, want in wants.items():
+        assert got[k].shape == want.shape
+        errs[k] = rel(got[k], want)
+        _record(fx["case"], k, errs[k], dtype)
+        print(fx["case"], dtype, k, "rel err vs reference golden", errs[k])
+    assert all(e < bound for e in errs.values()), (errs, bound)

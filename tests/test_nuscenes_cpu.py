@@ -52,43 +52,8 @@ def test_nuscenes_state_dict_is_drop_in(ref):
         assert r[k].shape == o[k].shape, k
 
 
-class _FakeEffNetFeatures(torch.nn.Module):
-    """Shape-compatible stand-in for the EfficientNet-B4 prefix (32/56/112 channels at strides 4/8/16):
-    the package is not installed, so real-weight parity exercises everything after the backbone."""
-
-    def __init__(self, H, W):
-        super().__init__()
-        self.output_shapes = [torch.Size((1, c, H // s, W // s)) for c, s in ((32, 4), (56, 8), (112, 16))]
-
-    def forward(self, x):
-        g = torch.Generator().manual_seed(7)
-        return [torch.randn(x.shape[0], *s[1:], generator=g) for s in self.output_shapes]
-
-
-def _load_shipped_ckpt():
-    import pickle
-    import types
-
-    class _Stub:
-        def __init__(self, *a, **k):
-            pass
-
-        def __setstate__(self, st):
-            self.__dict__.update(st if isinstance(st, dict) else {})
-
-    class _U(pickle.Unpickler):
-        def find_class(self, mod, name):
-            try:
-                return super().find_class(mod, name)
-            except Exception:
-                return type(name, (_Stub,), {})
-
-    pm = types.ModuleType("stub_pickle")
-    pm.Unpickler = _U
-    pm.load = lambda f, **kw: _U(f).load()
-    pm.__name__ = "pickle"
-    path = "/root/reference/nuscenes/logs/sinbevt_nuscenes_vehicle_50k.ckpt"
-    return torch.load(path, map_location="cpu", weights_only=False, pickle_module=pm)["state_dict"]
+_FakeEffNetFeatures = nc.FakeEffNetFeatures
+_load_shipped_ckpt = nc.load_shipped_ckpt
 
 
 def test_real_weights_shipped_checkpoint(ref):
