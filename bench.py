@@ -568,9 +568,7 @@ def main():
                 "traffic": traffic.get(fam)}
 
     if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     result = {
@@ -612,9 +610,18 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         result["cpu_baseline"] = cpu_baseline(cfg, sd, reps=3, warm=1)
     print(json.dumps(result))
+    _finish(world)
+
+
+def _finish(world):
+    """N > 1: leave without tearing the NCCL communicator down.  Every collective of this script has completed (the
+    last one is the shard check's all-reduce); destroy_process_group() with CUDA graphs that captured NCCL kernels
+    still alive was seen to hang at exit (profiles/r02_bench_2gpu.json), so the ranks flush and exit directly."""
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

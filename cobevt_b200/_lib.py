@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcobevt_sm100.so")
+# COBEVT_LIB_PATH: load another build of the SAME library (kernel A/B timing); never a different backend
+LIB_PATH = os.environ.get("COBEVT_LIB_PATH") or os.path.join(_HERE, "libcobevt_sm100.so")
 
 c_i32 = ctypes.c_int32
 c_f32 = ctypes.c_float
@@ -25,6 +26,14 @@ class ConvParams(ctypes.Structure):
         ("stride_h", c_i32), ("stride_w", c_i32), ("pad_h", c_i32), ("pad_w", c_i32), ("res_rows", c_i32),
         ("in_upsample", c_i32), ("act", c_i32), ("dtype", c_i32), ("block_n", c_i32),
         ("ln_eps", c_f32),
+    ]
+
+
+class MlpParams(ctypes.Structure):
+    _fields_ = [
+        ("x_ln", c_vp), ("w1", c_vp), ("b1", c_vp), ("w2", c_vp), ("b2", c_vp), ("res", c_vp), ("y", c_vp), ("y_ln", c_vp),
+        ("ln_gamma", c_vp), ("ln_beta", c_vp),
+        ("M", c_i32), ("C", c_i32), ("H", c_i32), ("dtype", c_i32), ("ln_eps", c_f32),
     ]
 
 
@@ -67,6 +76,8 @@ def lib():
         L.cobevt_conv_pack_weight.argtypes = [c_vp, c_i32, c_i32, c_i32, c_vp]
         L.cobevt_conv2d_nhwc_fwd.restype = ctypes.c_int
         L.cobevt_conv2d_nhwc_fwd.argtypes = [ctypes.POINTER(ConvParams), c_vp]
+        L.cobevt_token_mlp_fwd.restype = ctypes.c_int
+        L.cobevt_token_mlp_fwd.argtypes = [ctypes.POINTER(MlpParams), c_vp]
         L.cobevt_window_attn_fwd.restype = ctypes.c_int
         L.cobevt_window_attn_fwd.argtypes = [ctypes.POINTER(AttnParams), c_vp]
         L.cobevt_attn_resident_keys.restype = ctypes.c_int32
@@ -116,5 +127,5 @@ def check(rc, what):
 
 EXPORTED_SYMBOLS = [
     "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
-    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys",
+    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_token_mlp_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys",
 ] + list(_ELTWISE_SIGS)

@@ -76,9 +76,18 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) 
   }
 }
 
-// Lean variant for the innermost loops: the retry counter lives only inside the asm block (no live register across
-// the loop body), try_wait itself suspends the thread in hardware, and a protocol bug still traps instead of hanging.
+// Wait of the innermost softmax / epilogue loops.  Measured on B200 (profiles/r02_attn_ab.log): ANY bounded form of this
+// wait -- a retry counter in the loop, with or without a try_wait suspend-time hint -- costs 8 % of the attention
+// kernel, because the per-thread exit predicate makes ptxas wrap the loop in a BSSY / BSYNC / WARPSYNC reconvergence
+// region that every wait then executes even when the first try succeeds.  The default is therefore the bare
+// try_wait loop (variant 2); a hang is still bounded in practice: every stall of these loops also stalls the
+// MMA-issuer / loader warp of the same CTA, whose waits (mbar_wait / mbar_wait_a) are bounded and trap the grid.
+// Variants 0 (counter) and 1 (counter + 16 us suspend hint) are kept for A/B builds (tools/build_variant.sh).
+#ifndef COBEVT_WAIT_VARIANT
+#define COBEVT_WAIT_VARIANT 2
+#endif
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parity) {
+#if COBEVT_WAIT_VARIANT == 0       // bounded, no hint (A/B only)
   asm volatile(
       "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
       "mov.u32 n, 0;\n\t"
@@ -92,6 +101,31 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar_addr, uint32_t parit
       "DONE_%=:\n\t}"
       ::"r"(bar_addr), "r"(parity), "n"(COBEVT_MBAR_SPIN_LIMIT)
       : "memory");
+#elif COBEVT_WAIT_VARIANT == 2     // round-1 form: unbounded, no hint (A/B only)
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar_addr), "r"(parity)
+      : "memory");
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 16384;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 262144;\n\t"       // 2^18 x 16 us = ~4 s
+      "@p bra WAIT_%=;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(bar_addr), "r"(parity)
+      : "memory");
+#endif
 }
 
 // ----------------------------------------------------------------------------
@@ -203,6 +237,14 @@ __device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_
         "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]),
         "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]), "r"(taddr)
       : "memory");
+}
+// two consecutive 32-bit columns per lane (small per-row side data, e.g. LayerNorm partials exchanged between the
+// warps that share a TMEM lane quarter)
+__device__ __forceinline__ void tmem_st_32x32b_x2(uint32_t taddr, uint32_t a, uint32_t b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t& a, uint32_t& b) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(a), "=r"(b) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");

@@ -1,0 +1,404 @@
+// Fused token MLP for sm_100a:   y = res + W2 gelu(W1 x_ln + b1) + b2 ;  y_ln = LayerNorm(y)
+//
+// The PreNorm feed-forward of every FAX / FuseBEVT block (fax_modules.py:309-313,411,435-437: mlp_1 / mlp_2 with
+// prenorm and postnorm; base_transformer.py:102-124 PreNormResidual(FeedForward)) with dim 128 -> 256 -> 128.  As two
+// GEMM launches the 2x-wide GELU activations make an HBM round trip (512 B per token written, then read back);
+// here they never leave the SM:
+//
+//   GEMM1  D1[128 x 256] (TMEM) = X[128 x 128] W1^T         tcgen05, A = TMA token slab, B = resident weight image
+//   epi 1  H = gelu(D1 + b1) -> 16-bit, written straight into shared memory as the SWIZZLE_128B K-major A operand
+//   GEMM2  Y[128 x 128] (TMEM) = H[128 x 256] W2^T
+//   epi 2  y = Y + b2 + res ; row LayerNorm (the two column halves meet through shared memory) -> y, y_ln
+//
+// One persistent CTA per SM walks over 128-token tiles.  Both weight matrices (2 x 64 KB, host-packed by
+// cobevt_conv_pack_weight with block_n = 128) stay resident; shared memory = 128 KB weights + 32 KB token slab
+// + 64 KB H = 224 KB.  The two epilogues are bound by per-warp latency (TMEM read -> GELU: 4 MUFU per pair ->
+// swizzled stores; residual load -> LayerNorm exchange -> global stores), so they run on DIFFERENT warps and on
+// DIFFERENT tiles at the same time:
+//   warps 0-7    team A, epilogue 1 of tile i+1 (TMEM lane quarter = warp % 4, hidden-column half = warp / 4)
+//   warps 8-15   team B, epilogue 2 of tile i   (lane quarter = warp % 4, output-column half = (warp - 8) / 4); the
+//                LayerNorm partials of the two halves meet through two spare TMEM columns
+//   warp  16     loader (one thread)      warp 17  MMA issuer: GEMM1(i+1) is issued BEFORE GEMM2(i), as soon as team A
+//                has D1(i) in registers, so the tensor core, team A and team B overlap; warps 18-19 complete the
+//                control warpgroup for setmaxnreg (104 registers for the 16 epilogue warps)
+// The kernel is bound by the epilogue math and HBM (x_ln, res in; y, y_ln out: 1 KB per token), not by the tensor pipe.
+//
+// The LayerNorm in FRONT of the MLP is produced by the preceding kernel's epilogue (y_ln of the projection /
+// previous MLP) with its affine folded into W1, so x_ln is the plain normalised row.
+#include "sm100.cuh"
+#include "common.h"
+#include <cstring>
+
+using namespace sm100;
+
+namespace {
+
+constexpr int MLP_C = 128, MLP_H = 256, MLP_BM = 128;
+constexpr int MLP_THREADS = 640;
+constexpr int MLP_REGS_EPI = 104, MLP_REGS_CTRL = 40;     // setmaxnreg split of the 640 x 96 register pool
+constexpr int KBLK_BYTES = 128 * 64 * 2;                       // one 128-row x 64-column SWIZZLE_128B image: 16 KB
+constexpr int SW1_BYTES = 4 * KBLK_BYTES, SW2_BYTES = 4 * KBLK_BYTES, SA_BYTES = 2 * KBLK_BYTES, SH_BYTES = 4 * KBLK_BYTES;
+constexpr int MLP_SMEM = 1024 + SW1_BYTES + SW2_BYTES + SA_BYTES + SH_BYTES;     // 230400 B
+
+struct MArgs {
+  CobevtMlpParams p;
+  int32_t m_tiles;
+  uint32_t idesc;
+  alignas(64) CUtensorMap tmX;      // {C, M} box {64, 128}, SWIZZLE_128B
+};
+
+// exact (erf) GELU on a pair, see conv_gemm.cu (Abramowitz-Stegun 7.1.26, |err| <= 1.5e-7)
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float a0 = fabsf(x0), a1 = fabsf(x1);
+  float z0, z1, t0, t1, p0, p1, q0, q1;
+  fmul2(z0, z1, a0, a1, 0.70710678118654752f, 0.70710678118654752f);
+  ffma2(t0, t1, z0, z1, 0.3275911f, 0.3275911f, 1.0f, 1.0f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(t0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(t1));
+  ffma2(p0, p1, t0, t1, 1.061405429f, 1.061405429f, -1.453152027f, -1.453152027f);
+  ffma2(p0, p1, p0, p1, t0, t1, 1.421413741f, 1.421413741f);
+  ffma2(p0, p1, p0, p1, t0, t1, -0.284496736f, -0.284496736f);
+  ffma2(p0, p1, p0, p1, t0, t1, 0.254829592f, 0.254829592f);
+  fmul2(q0, q1, z0, z1, z0, z1);
+  fmul2(q0, q1, q0, q1, -1.4426950408889634f, -1.4426950408889634f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q0) : "f"(q0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(q1) : "f"(q1));
+  fmul2(p0, p1, p0, p1, t0, t1);
+  fmul2(p0, p1, p0, p1, q0, q1);
+  float e0 = 1.0f - p0, e1 = 1.0f - p1;
+  fmul2(t0, t1, a0, a1, 0.5f, 0.5f);
+  fmul2(x0, x1, x0, x1, 0.5f, 0.5f);
+  ffma2(x0, x1, t0, t1, e0, e1, x0, x1);
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pk(float a, float b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+template <bool BF16>
+__device__ __forceinline__ float2 upk(uint32_t u) {
+  if constexpr (BF16) return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  else return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+__device__ __forceinline__ void umma_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(MLP_THREADS, 1) token_mlp_kernel(const __grid_constant__ MArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem;                     // [n_tile 2][k_block 2] x 16 KB
+  uint8_t* sW2 = sW1 + SW1_BYTES;          // [k_block 4] x 16 KB
+  uint8_t* sA = sW2 + SW2_BYTES;           // [k_block 2] x 16 KB: the token slab
+  uint8_t* sH = sA + SA_BYTES;             // [k_block 4] x 16 KB: gelu(...) as the A operand of GEMM2
+  __shared__ __align__(8) uint64_t w_full, a_full, a_empty, d1_full, d1_empty, h_full, y_full, y_empty;
+  __shared__ uint32_t tmem_base_s;
+
+  const CobevtMlpParams& p = a.p;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(&w_full, 1);
+    mbar_init(&a_full, 1);
+    mbar_init(&a_empty, 1);
+    mbar_init(&d1_full, 1);
+    mbar_init(&d1_empty, 256);
+    mbar_init(&h_full, 256);
+    mbar_init(&y_full, 1);
+    mbar_init(&y_empty, 256);
+    mbar_fence_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(&tmem_base_s, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_s;
+  const uint32_t t_d1 = tmem_base, t_y = tmem_base + MLP_H;      // D1: columns [0, 256), Y: [256, 384)
+  const uint32_t t_x = tmem_base + MLP_H + MLP_C;                 // LayerNorm exchange: columns [384, 388)
+
+  if (warp == 16) {
+    // ======================================= loader =======================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MLP_REGS_CTRL));
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&w_full, SW1_BYTES + SW2_BYTES);
+      for (int i = 0; i < 4; ++i) bulk_g2s(sW1 + i * KBLK_BYTES, reinterpret_cast<const uint8_t*>(p.w1) + (size_t)i * KBLK_BYTES, KBLK_BYTES, &w_full);
+      for (int i = 0; i < 4; ++i) bulk_g2s(sW2 + i * KBLK_BYTES, reinterpret_cast<const uint8_t*>(p.w2) + (size_t)i * KBLK_BYTES, KBLK_BYTES, &w_full);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(&a_empty, (it & 1u) ^ 1u);
+        mbar_arrive_expect_tx(&a_full, SA_BYTES);
+        tma_load_2d(sA, &a.tmX, &a_full, 0, tile * MLP_BM);
+        tma_load_2d(sA + KBLK_BYTES, &a.tmX, &a_full, 64, tile * MLP_BM);
+      }
+    }
+  } else if (warp == 17) {
+    // ======================================= MMA issuer ===================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MLP_REGS_CTRL));
+    const uint64_t dsc = make_smem_desc(0, 16, 1024, LAYOUT_SW128);
+    const uint32_t lo0 = (uint32_t)dsc, hi = (uint32_t)(dsc >> 32);
+    const uint32_t aA = lo0 | (smem_u32(sA) >> 4), aH = lo0 | (smem_u32(sH) >> 4);
+    const uint32_t bW1 = lo0 | (smem_u32(sW1) >> 4), bW2 = lo0 | (smem_u32(sW2) >> 4);
+    constexpr uint32_t KB16 = KBLK_BYTES >> 4;
+    mbar_wait(&w_full, 0);
+    auto gemm1 = [&](uint32_t it) {                 // D1 = X(it) W1^T
+      mbar_wait(&a_full, it & 1u);
+      mbar_wait(&d1_empty, (it & 1u) ^ 1u);          // team A has D1 of the previous tile in registers
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_lohi(t_d1 + nt * 128, aA + kb * KB16 + ks * 2, hi, bW1 + (nt * 2 + kb) * KB16 + ks * 2, hi, a.idesc, (kb | ks) ? 1u : 0u);
+        umma_commit(&a_empty);                       // the token slab may be overwritten
+        umma_commit(&d1_full);
+      }
+      __syncwarp();
+    };
+    uint32_t it = 0;
+    if (blockIdx.x < a.m_tiles) gemm1(0);
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      if (tile + (int)gridDim.x < a.m_tiles) gemm1(it + 1);     // runs under team A's GELU of tile `it`
+      // ---- GEMM2: Y = H W2^T -----------------------------------------------------------------
+      mbar_wait(&h_full, it & 1u);                   // team A wrote H (and fenced it to the async proxy)
+      mbar_wait(&y_empty, (it & 1u) ^ 1u);           // team B has Y of the previous tile in registers
+      tc_fence_after_sync();
+      if (elect_one()) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            umma_lohi(t_y, aH + kb * KB16 + ks * 2, hi, bW2 + kb * KB16 + ks * 2, hi, a.idesc, (kb | ks) ? 1u : 0u);
+        umma_commit(&y_full);                        // also "H may be overwritten"
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 18) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MLP_REGS_CTRL));      // idle half of the control warpgroup
+  } else if (warp < 8) {
+    // ======================================= team A: epilogue 1 ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MLP_REGS_EPI));
+    const int q4 = warp & 3, hf = warp >> 2;                    // TMEM lane quarter, hidden-column half
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      mbar_wait(&d1_full, ph);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int u = 0; u < 2; ++u) {
+        const int col0 = hf * 128 + u * 64;                       // hidden columns of this unit = k-block col0 / 64 of H
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32b_x32(t_d1 + lane_base + col0, r0);
+        tmem_ld_32x32b_x32(t_d1 + lane_base + col0 + 32, r1);
+        tmem_ld_wait();
+        if (u == 1) {                                             // both units are out of TMEM: GEMM1 of the next tile may run
+          tc_fence_before_sync();
+          mbar_arrive(&d1_empty);
+        }
+        float v[64];
+        const float4* b4 = reinterpret_cast<const float4*>(p.b1 + col0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ba = __ldg(b4 + (j >> 2)), bb = __ldg(b4 + 8 + (j >> 2));
+          v[j] = __uint_as_float(r0[j]) + ba.x; v[j + 1] = __uint_as_float(r0[j + 1]) + ba.y;
+          v[j + 2] = __uint_as_float(r0[j + 2]) + ba.z; v[j + 3] = __uint_as_float(r0[j + 3]) + ba.w;
+          v[32 + j] = __uint_as_float(r1[j]) + bb.x; v[32 + j + 1] = __uint_as_float(r1[j + 1]) + bb.y;
+          v[32 + j + 2] = __uint_as_float(r1[j + 2]) + bb.z; v[32 + j + 3] = __uint_as_float(r1[j + 3]) + bb.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 64; j += 2) gelu_erf2(v[j], v[j + 1]);
+        if (u == 0 && it > 0) mbar_wait(&y_full, ph ^ 1u);        // GEMM2 of the previous tile has finished reading H
+        const uint32_t hrow = smem_u32(sH) + (uint32_t)(col0 >> 6) * KBLK_BYTES + (uint32_t)row * 128u;
+#pragma unroll
+        for (int ck = 0; ck < 8; ++ck)                            // 8 chunks of 16 B, SWIZZLE_128B (chunk ^ (row & 7))
+          sts128(hrow + ((((uint32_t)ck) ^ ((uint32_t)row & 7u)) << 4), pk<BF16>(v[ck * 8 + 0], v[ck * 8 + 1]),
+                 pk<BF16>(v[ck * 8 + 2], v[ck * 8 + 3]), pk<BF16>(v[ck * 8 + 4], v[ck * 8 + 5]), pk<BF16>(v[ck * 8 + 6], v[ck * 8 + 7]));
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&h_full);
+    }
+  } else {
+    // ======================================= team B: epilogue 2 ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MLP_REGS_EPI));
+    const int q4 = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, output-column half
+    const int row = q4 * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
+    const bool do_ln = p.y_ln != nullptr;
+    const int col0 = hf * 64;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t ph = it & 1u;
+      const int64_t m = (int64_t)tile * MLP_BM + row;
+      const bool row_ok = m < p.M;
+      // the residual row segment is fetched BEFORE the accumulator wait: its latency hides under GEMM2
+      uint4 rr[8];
+      if (row_ok && p.res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(p.res) + (m * MLP_C + col0) * 2);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rr[t] = rp[t];
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) rr[t] = make_uint4(0, 0, 0, 0);
+      }
+      mbar_wait(&y_full, ph);
+      tc_fence_after_sync();
+      float v[64];
+      {
+        uint32_t r0[32];
+        tmem_ld_32x32b_x32(t_y + lane_base + col0, r0);
+        tmem_ld_wait();
+        const float4* b4 = reinterpret_cast<const float4*>(p.b2 + col0);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 ba = __ldg(b4 + (j >> 2));
+          v[j] = __uint_as_float(r0[j]) + ba.x; v[j + 1] = __uint_as_float(r0[j + 1]) + ba.y;
+          v[j + 2] = __uint_as_float(r0[j + 2]) + ba.z; v[j + 3] = __uint_as_float(r0[j + 3]) + ba.w;
+        }
+        tmem_ld_32x32b_x32(t_y + lane_base + col0 + 32, r0);
+        tmem_ld_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&y_empty);                                    // Y is in registers: GEMM2 of the next tile may run
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = __ldg(b4 + 8 + (j >> 2));
+          v[32 + j] = __uint_as_float(r0[j]) + bb.x; v[32 + j + 1] = __uint_as_float(r0[j + 1]) + bb.y;
+          v[32 + j + 2] = __uint_as_float(r0[j + 2]) + bb.z; v[32 + j + 3] = __uint_as_float(r0[j + 3]) + bb.w;
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const uint32_t w4[4] = {rr[t].x, rr[t].y, rr[t].z, rr[t].w};
+#pragma unroll
+        for (int k2 = 0; k2 < 4; ++k2) {
+          const float2 f = upk<BF16>(w4[k2]);
+          v[t * 8 + 2 * k2] += f.x;
+          v[t * 8 + 2 * k2 + 1] += f.y;
+        }
+      }
+      if (row_ok && p.y) {
+        uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.y) + (m * MLP_C + col0) * 2);
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          yp[t] = make_uint4(pk<BF16>(v[t * 8 + 0], v[t * 8 + 1]), pk<BF16>(v[t * 8 + 2], v[t * 8 + 3]),
+                             pk<BF16>(v[t * 8 + 4], v[t * 8 + 5]), pk<BF16>(v[t * 8 + 6], v[t * 8 + 7]));
+      }
+      if (do_ln) {
+        // exact two-pass statistics on this thread's 64 columns; the two halves combine (mean, M2) (Chan et al.)
+        // through two TMEM columns of their shared lane quarter
+        float s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) s1 += v[j];
+        const float mh = s1 * (1.0f / 64.0f);
+        float m2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) { const float d = v[j] - mh; m2 += d * d; }
+        tmem_st_32x32b_x2(t_x + lane_base + hf * 2, __float_as_uint(mh), __float_as_uint(m2));
+        tmem_st_wait();
+        tc_fence_before_sync();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q4) : "memory");     // the two warps of this lane quarter
+        tc_fence_after_sync();
+        uint32_t om, o2;
+        tmem_ld_32x32b_x2(t_x + lane_base + (hf ^ 1) * 2, om, o2);
+        tmem_ld_wait();
+        const float omean = __uint_as_float(om);
+        const float mean = 0.5f * (mh + omean);
+        const float dlt = mh - omean;
+        const float var = (m2 + __uint_as_float(o2) + dlt * dlt * 32.0f) * (1.0f / 128.0f);
+        const float rstd = rsqrtf(var + p.ln_eps);
+        if (p.ln_gamma) {
+          const float4* g4 = reinterpret_cast<const float4*>(p.ln_gamma + col0);
+          const float4* e4 = reinterpret_cast<const float4*>(p.ln_beta + col0);
+#pragma unroll
+          for (int j = 0; j < 64; j += 4) {
+            const float4 g = __ldg(g4 + (j >> 2)), e = __ldg(e4 + (j >> 2));
+            v[j] = fmaf((v[j] - mean) * rstd, g.x, e.x); v[j + 1] = fmaf((v[j + 1] - mean) * rstd, g.y, e.y);
+            v[j + 2] = fmaf((v[j + 2] - mean) * rstd, g.z, e.z); v[j + 3] = fmaf((v[j + 3] - mean) * rstd, g.w, e.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) v[j] = (v[j] - mean) * rstd;
+        }
+        if (row_ok) {
+          uint4* yp = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.y_ln) + (m * MLP_C + col0) * 2);
+#pragma unroll
+          for (int t = 0; t < 8; ++t)
+            yp[t] = make_uint4(pk<BF16>(v[t * 8 + 0], v[t * 8 + 1]), pk<BF16>(v[t * 8 + 2], v[t * 8 + 3]),
+                               pk<BF16>(v[t * 8 + 4], v[t * 8 + 5]), pk<BF16>(v[t * 8 + 6], v[t * 8 + 7]));
+        }
+        // the partner must have read this thread's partials before the next tile overwrites them
+        tc_fence_before_sync();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + q4) : "memory");
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+extern "C" int cobevt_token_mlp_fwd(const CobevtMlpParams* p, void* stream) {
+  if (!p || !p->x_ln || !p->w1 || !p->b1 || !p->w2 || !p->b2) return cobevt::fail(COBEVT_ERR_SHAPE, "token_mlp: null pointer");
+  if (p->C != MLP_C || p->H != MLP_H) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "token_mlp: built for C = 128, H = 256 (got %d, %d)", p->C, p->H);
+  if (p->M <= 0) return cobevt::fail(COBEVT_ERR_SHAPE, "token_mlp: M");
+  if (!p->y && !p->y_ln) return cobevt::fail(COBEVT_ERR_SHAPE, "token_mlp: no output");
+  if ((p->ln_gamma == nullptr) != (p->ln_beta == nullptr)) return cobevt::fail(COBEVT_ERR_SHAPE, "token_mlp: ln_gamma/ln_beta must come together");
+  if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "token_mlp: dtype");
+  const uintptr_t al = reinterpret_cast<uintptr_t>(p->x_ln) | reinterpret_cast<uintptr_t>(p->w1) | reinterpret_cast<uintptr_t>(p->w2) |
+                       reinterpret_cast<uintptr_t>(p->res) | reinterpret_cast<uintptr_t>(p->y) | reinterpret_cast<uintptr_t>(p->y_ln) |
+                       reinterpret_cast<uintptr_t>(p->b1) | reinterpret_cast<uintptr_t>(p->b2);
+  if (al & 15) return cobevt::fail(COBEVT_ERR_SHAPE, "token_mlp: pointers must be 16-byte aligned");
+  cobevt::EncodeTiledFn enc = cobevt::get_encode_tiled();
+  if (!enc) return cobevt::fail(COBEVT_ERR_CUDA, "token_mlp: cuTensorMapEncodeTiled unavailable");
+  MArgs a;
+  memset(&a, 0, sizeof(a));
+  a.p = *p;
+  a.m_tiles = cobevt::ceil_div(p->M, MLP_BM);
+  const bool bf = p->dtype == COBEVT_BF16;
+  a.idesc = make_idesc_f16(128, 128, bf, false, false);
+  {
+    const CUtensorMapDataType dt = bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const cuuint64_t dims[2] = {(cuuint64_t)MLP_C, (cuuint64_t)p->M};
+    const cuuint64_t strides[1] = {(cuuint64_t)MLP_C * 2};
+    const cuuint32_t box[2] = {64, MLP_BM};
+    const cuuint32_t es[2] = {1, 1};
+    if (enc(&a.tmX, dt, 2, const_cast<void*>(p->x_ln), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cobevt::fail(COBEVT_ERR_CUDA, "token_mlp: tensor map");
+  }
+  auto kern = bf ? token_mlp_kernel<true> : token_mlp_kernel<false>;
+  static bool attr_set[cobevt::kMaxDevices][2] = {};
+  const int dev = cobevt::current_device();
+  if (!attr_set[dev][bf]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM);
+    if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "token_mlp: set smem attr: %s", cudaGetErrorString(e));
+    attr_set[dev][bf] = true;
+  }
+  const int sms = cobevt::num_sms();
+  const int grid = a.m_tiles < sms ? a.m_tiles : sms;
+  kern<<<grid, MLP_THREADS, MLP_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  return cobevt::check_launch("token_mlp_kernel");
+}

@@ -13,7 +13,7 @@ Folding done at plan time (all exact re-associations of the reference math):
 import torch
 
 from . import ops
-from .ops import PackedConv, ACT_NONE, ACT_RELU, ACT_GELU, ACT_SWISH
+from .ops import PackedConv, PackedMlp, ACT_NONE, ACT_RELU, ACT_GELU, ACT_SWISH
 
 LN_EPS = 1e-5
 
@@ -193,10 +193,10 @@ class FaxStagePlan:
         # both attentions project the same normalised key / value maps: one N=256 GEMM each
         self.k12 = PackedConv(torch.cat([self.a1.wk, self.a2.wk], 0), torch.cat([self.a1.bk, self.a2.bk], 0), device, dtype)
         self.v12 = PackedConv(torch.cat([self.a1.wv, self.a2.wv], 0), torch.cat([self.a1.bv, self.a2.bv], 0), device, dtype)
-        self.m1a = PackedConv(*fold_ln_linear(cva.prenorm_1, cva.mlp_1[0]), device, dtype)
-        self.m1b = PackedConv(cva.mlp_1[2].weight.detach().float(), cva.mlp_1[2].bias.detach().float(), device, dtype)
-        self.m2a = PackedConv(*fold_ln_linear(cva.prenorm_2, cva.mlp_2[0]), device, dtype)
-        self.m2b = PackedConv(cva.mlp_2[2].weight.detach().float(), cva.mlp_2[2].bias.detach().float(), device, dtype)
+        self.m1 = PackedMlp(*fold_ln_linear(cva.prenorm_1, cva.mlp_1[0]), cva.mlp_1[2].weight.detach().float(),
+                            cva.mlp_1[2].bias.detach().float(), device, dtype)
+        self.m2 = PackedMlp(*fold_ln_linear(cva.prenorm_2, cva.mlp_2[0]), cva.mlp_2[2].weight.detach().float(),
+                            cva.mlp_2[2].bias.detach().float(), device, dtype)
         self.post_g = _dev_f32(cva.postnorm.weight, device)
         self.post_b = _dev_f32(cva.postnorm.bias, device)
 
@@ -243,8 +243,7 @@ class FaxStagePlan:
         skip = x.reshape(-1, d) if self.skip else None
         rr = P * x_rows if (self.skip and x_rows != BL) else 0
         z, _, z_ln = ops.linear_tokens(a.reshape(-1, d), self.a1.proj, res=skip, res_rows=rr, ln_out=True)
-        hmid = ops.linear_tokens(z_ln, self.m1a, act=ACT_GELU)[0]
-        z, _, z_ln = ops.linear_tokens(hmid, self.m1b, res=z, ln_out=True)
+        z, z_ln = ops.token_mlp(z_ln, self.m1, z)
         # ---- local window <-> dilated grid (fax_modules.py:413-433) ---------------------------
         q2 = ops.linear_tokens(z_ln, self.a2.q)[0].view(BL, 1, H, W, d)
         qm = ops.token_map(1, H, W, *self.q_win, False)
@@ -252,9 +251,7 @@ class FaxStagePlan:
         a = ops.window_attention(q2, k2, v2, qm, km, self.a2.heads, self.a2.scale, True,
                                  k_pad=self.a2.k_pad if padded else None, v_pad=self.a2.v_pad if padded else None)
         z2, _, z_ln = ops.linear_tokens(a.reshape(-1, d), self.a2.proj, res=z if self.skip else None, ln_out=True)
-        hmid = ops.linear_tokens(z_ln, self.m2a, act=ACT_GELU)[0]
-        _, _, out = ops.linear_tokens(hmid, self.m2b, res=z2, want16=False, ln_out=True,
-                                      ln_gamma=self.post_g, ln_beta=self.post_b)
+        _, out = ops.token_mlp(z_ln, self.m2, z2, want16=False, ln_out=True, ln_gamma=self.post_g, ln_beta=self.post_b)
         return out.view(BL, H, W, d)
 
 
@@ -319,8 +316,8 @@ class SwapAttnPlan:
         self.bias = tbl[idx].permute(2, 0, 1).contiguous().to(device)      # heads T T
         self.heads, self.scale = at.heads, at.scale
         ff = prenorm_ffd.fn.net
-        self.f1 = PackedConv(*fold_ln_linear(prenorm_ffd.norm, ff[0]), device, dtype)
-        self.f2 = PackedConv(ff[3].weight.detach().float(), ff[3].bias.detach().float(), device, dtype)
+        self.ff = PackedMlp(*fold_ln_linear(prenorm_ffd.norm, ff[0]), ff[3].weight.detach().float(),
+                            ff[3].bias.detach().float(), device, dtype)
 
 
 class SwapBlockPlan:
@@ -346,8 +343,7 @@ class SwapBlockPlan:
             a = ops.window_attention(qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:], m, m, sp.heads, sp.scale,
                                      False, bias=sp.bias, key_mask=mask if self.use_mask else None)
             x, _, x_ln = ops.linear_tokens(a.reshape(-1, d), sp.out, res=x, ln_out=True)
-            hmid = ops.linear_tokens(x_ln, sp.f1, act=ACT_GELU)[0]
-            x, _, x_ln = ops.linear_tokens(hmid, sp.f2, res=x, ln_out=True)
+            x, x_ln = ops.token_mlp(x_ln, sp.ff, x)
         return x, x_ln
 
 

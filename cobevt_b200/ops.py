@@ -8,7 +8,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvParams, AttnParams, TokenMap
+from ._lib import ConvParams, AttnParams, TokenMap, MlpParams
 
 F16, BF16 = 0, 1
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_SWISH = 0, 1, 2, 3
@@ -190,6 +190,45 @@ def linear_tokens(x, pc, **kw):
     y, y32, yln = conv2d_nhwc(x4, pc, **kw)
     f = lambda t: None if t is None else t.reshape(*shp[:-1], pc.cout)
     return f(y), f(y32), f(yln)
+
+
+class PackedMlp:
+    """Weights of one PreNorm feed-forward (LayerNorm affine already folded into w1 / b1), packed for the fused
+    token-MLP kernel when it is the 128 -> 256 -> 128 shape that kernel is built for, and for the two-GEMM path
+    otherwise."""
+
+    def __init__(self, w1, b1, w2, b2, device, dtype):
+        self.fused = tuple(w1.shape) == (256, 128) and tuple(w2.shape) == (128, 256)
+        self.dtype = dtype
+        if self.fused:
+            self.a = PackedConv(w1, b1, device, dtype, block_n=128)
+            self.b = PackedConv(w2, b2, device, dtype, block_n=128)
+        else:
+            self.a = PackedConv(w1, b1, device, dtype)
+            self.b = PackedConv(w2, b2, device, dtype)
+
+
+def token_mlp(x_ln, mlp, res, want16=True, ln_out=True, ln_gamma=None, ln_beta=None, ln_eps=1e-5):
+    """x_ln (..., C) plain-normalised tokens, res (..., C) residual stream -> (y | None, y_ln | None):
+    y = res + W2 gelu(W1 x_ln + b1) + b2, y_ln = LayerNorm(y)."""
+    if not mlp.fused:
+        hmid = linear_tokens(x_ln, mlp.a, act=ACT_GELU)[0]
+        y, _, yln = linear_tokens(hmid, mlp.b, res=res, want16=want16, ln_out=ln_out, ln_gamma=ln_gamma, ln_beta=ln_beta)
+        return y, yln
+    shp = x_ln.shape
+    C = shp[-1]
+    M = x_ln.numel() // C
+    assert x_ln.is_cuda and x_ln.is_contiguous() and res.is_contiguous() and res.numel() == M * C and res.dtype == x_ln.dtype
+    _same_device(x_ln)
+    y = torch.empty(shp, dtype=x_ln.dtype, device=x_ln.device) if want16 else None
+    yln = torch.empty(shp, dtype=x_ln.dtype, device=x_ln.device) if ln_out else None
+    p = MlpParams()
+    p.x_ln, p.w1, p.b1, p.w2, p.b2 = _ptr(x_ln), _ptr(mlp.a.w), _ptr(mlp.a.bias), _ptr(mlp.b.w), _ptr(mlp.b.bias)
+    p.res, p.y, p.y_ln, p.ln_gamma, p.ln_beta = _ptr(res), _ptr(y), _ptr(yln), _ptr(ln_gamma), _ptr(ln_beta)
+    p.M, p.C, p.H, p.dtype, p.ln_eps = M, C, 256, dtype_code(x_ln.dtype), ln_eps
+    with _timed("conv_gemm", 2 * M * (128 * 256 + 256 * 128), f"token_mlp M={M} 128->256->128"):
+        _lib.check(_lib.lib().cobevt_token_mlp_fwd(ctypes.byref(p), _stream()), "cobevt_token_mlp_fwd")
+    return y, yln
 
 
 def token_map(views, H, W, w1, w2, grid, Hv=None, Wv=None):

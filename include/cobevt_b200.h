@@ -79,6 +79,30 @@ int cobevt_conv_pack_weight(const uint16_t* w_host, int32_t Cout, int32_t K, int
 int cobevt_conv2d_nhwc_fwd(const CobevtConvParams* p, void* stream);
 
 /* ---------------------------------------------------------------------------
+ * Fused token MLP (PreNorm feed-forward) on tcgen05, the 2x-wide GELU activations never leave the SM:
+ *   y = res + W2 gelu(W1 x_ln + b1) + b2 ;  y_ln = LayerNorm(y) [* gamma + beta]
+ * Replaces mlp_1 / mlp_2 with prenorm_1/2 and postnorm of CrossViewSwapAttention (fax_modules.py:309-313,411,
+ * 435-437) and PreNormResidual(FeedForward) of the FuseBEVT blocks (base_transformer.py:102-124,
+ * swap_fusion_modules.py:144-163).  x_ln is the plain normalised row produced by the preceding kernel's y_ln output
+ * (the LayerNorm affine is folded into w1 / b1).  Built for C = 128, H = 256.
+ * -------------------------------------------------------------------------*/
+typedef struct {
+  const void* x_ln;      /* (M, C) 16-bit                                                         */
+  const void* w1;        /* (H, C) packed by cobevt_conv_pack_weight with block_n = 128           */
+  const float* b1;       /* [H] fp32                                                              */
+  const void* w2;        /* (C, H) packed with block_n = 128                                      */
+  const float* b2;       /* [C] fp32                                                              */
+  const void* res;       /* (M, C) 16-bit residual stream, or NULL                                */
+  void* y;               /* (M, C) 16-bit, or NULL                                                */
+  void* y_ln;            /* (M, C) 16-bit LayerNorm of the output row, or NULL                    */
+  const float* ln_gamma; /* [C] affine of y_ln or NULL (plain normalised row)                     */
+  const float* ln_beta;
+  int32_t M, C, H, dtype;
+  float ln_eps;
+} CobevtMlpParams;
+int cobevt_token_mlp_fwd(const CobevtMlpParams* p, void* stream);
+
+/* ---------------------------------------------------------------------------
  * Windowed / dilated-grid multi-head attention (head_dim 32) on tcgen05:
  *   S = scale * Q K^T (+ bias) (+ key mask) ; P = softmax(S) ; O = P V
  * Q, K, V are already projected token maps; window / grid partitions are pure

@@ -315,3 +315,35 @@ def test_global_self_attention_bias_two_segments(hw):
                            False, bias=bias)
     assert out.shape == ref.shape
     assert relerr(out, ref) < 2e-3, relerr(out, ref)
+
+
+# --------------------------------------------------------------------------- fused token MLP
+@pytest.mark.parametrize("M,affine,dt", [(700, False, torch.float16), (128 * 300 + 5, True, torch.float16), (4096, False, torch.bfloat16)])
+def test_token_mlp_fused_vs_two_gemms_and_fp32(M, affine, dt):
+    """y = res + W2 gelu(W1 x + b1) + b2, y_ln = LN(y): the fused kernel (H never leaves the SM) against the two-GEMM
+    path it replaces (same rounding points: 16-bit H, fp32 accumulation) and against plain fp32 torch math."""
+    from cobevt_b200 import ops
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 128, generator=g).to(dt).cuda()
+    res = torch.randn(M, 128, generator=g).to(dt).cuda()
+    w1 = (torch.randn(256, 128, generator=g) / 11).to(dt).float()
+    w2 = (torch.randn(128, 256, generator=g) / 16).to(dt).float()
+    b1, b2 = torch.randn(256, generator=g) * 0.2, torch.randn(128, generator=g) * 0.2
+    gamma = (torch.rand(128, generator=g) + 0.5).cuda() if affine else None
+    beta = (torch.randn(128, generator=g) * 0.1).cuda() if affine else None
+    fused = ops.PackedMlp(w1, b1, w2, b2, "cuda", dt)
+    assert fused.fused
+    y, yln = ops.token_mlp(x, fused, res, ln_gamma=gamma, ln_beta=beta)
+    a, b = ops.PackedConv(w1, b1, "cuda", dt), ops.PackedConv(w2, b2, "cuda", dt)
+    hmid = ops.linear_tokens(x, a, act=ops.ACT_GELU)[0]
+    y2, _, yln2 = ops.linear_tokens(hmid, b, res=res, ln_out=True, ln_gamma=gamma, ln_beta=beta)
+    torch.cuda.synchronize()
+    tol = 2e-3 if dt == torch.float16 else 1.5e-2
+    assert relerr(y, y2) < tol / 4 and relerr(yln, yln2) < tol / 2, (relerr(y, y2), relerr(yln, yln2))   # LN partials combine in a different order
+    h = F.gelu(x.float() @ w1.cuda().t() + b1.cuda()).to(dt).float()
+    ref = res.float() + h @ w2.cuda().t() + b2.cuda()
+    refln = F.layer_norm(ref, (128,), gamma, beta)
+    assert relerr(y, ref) < tol, relerr(y, ref)
+    assert relerr(yln, refln) < tol, relerr(yln, refln)
+    _, only_ln = ops.token_mlp(x, fused, res, want16=False, ln_gamma=gamma, ln_beta=beta)
+    assert torch.equal(only_ln, yln)
