@@ -45,9 +45,7 @@ struct AArgs {
   uint32_t idesc_qk, idesc_pv;
   int32_t kv_vt, kv_segs;             // views of the K/V tensors (batch stride in views); key segments per launch
   int32_t bias_ld;                    // keys per bias row = keys of the WHOLE window (all segments); == Lk without segments
-  int32_t kv_tma;                     // resident K / V windows are fetched by 4-D TMA tensor loads
-  int32_t kv_box_views, kv_nbox;      // the K window arrives as kv_nbox boxes of kv_box_views views, each with its own barrier:
-                                      // S = Q K^T of the first chunks starts after the first box, not after the whole window
+  int32_t kv_tma;                     // resident K / V windows are fetched by two 4-D TMA tensor loads
   alignas(64) CUtensorMap tmK, tmV;   // {C, Wv, Hv, B*views}, box {32, w2 (span), w1 (span), views}, SWIZZLE_64B
 };
 
@@ -878,10 +876,6 @@ constexpr int V3_THREADS = (V3_WG + 1) * 128;            // 640
 constexpr int V3_REGS_SOFTMAX = 112, V3_REGS_ISSUER = 32;   // the CTA pool is 640 x 96 = 61440 = 16*32*112 + 4*32*32
 constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 16 KB: one P buffer per warpgroup
 constexpr int V3_POLY_DEFAULT = 0;     // measured: 0 / 25 % / 37.5 % within noise, 50 % slower (profiles/r02_attn_ab.log)
-#ifndef COBEVT_KV_BOXES
-#define COBEVT_KV_BOXES 0              // 1: the K window lands as several TMA boxes with their own barriers (A/B builds: no gain,
-                                       // profiles/r02_attn_kbox_ab.log); 0: one box
-#endif
 __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + SP3_BYTES); }
 
 // POLY: bit cc set -> the 8 exponentials of 8-key group cc (of the 8 groups of a 64-key chunk) use poly_exp2_pair
@@ -898,9 +892,11 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   float* kmask = reinterpret_cast<float*>(sV + keys_pad * 64);
   __shared__ __align__(8) uint64_t bars[V3_WG][8];          // per warpgroup: S F | O - | P - | Q0 Q1
   enum : uint32_t { BAR_S = 0, BAR_F = 8, BAR_O = 16, BAR_P = 32, BAR_Q = 48 };
-  constexpr int MAX_KBOX = 8;
-  __shared__ __align__(8) uint64_t bar_k[MAX_KBOX], bar_v;  // K boxes / V window landed (TMA path): S = Q K^T starts as soon as
-                                                            // the first K box is in, the rest of K and V stream under the first softmax
+  __shared__ __align__(8) uint64_t bar_k, bar_v;            // K / V windows landed (TMA path): S = Q K^T starts as soon as K
+                                                            // is in, the V window keeps streaming under the first softmax.
+  // This kernel sits at its register limit (112 / 32 after setmaxnreg): two further changes were measured SLOWER and
+  // removed -- K as several TMA boxes with their own barriers (-4 %, profiles/r02_attn_kbox_ab.log) and fetching the dense
+  // bias of a chunk before the S wait (-60 %: 490 more spill bytes land in every path, profiles/r02_attn_bias_prefetch_ab.log)
   __shared__ float2 sML[V3_WG][TILE_Q];                     // (running max, sum) partials of the key-split merge
   __shared__ uint32_t tmem_base_s;
 
@@ -922,22 +918,17 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       for (int j = 0; j < 2; ++j) {
         mbar_init(&bars[i][j], j == 0 ? 1 : 128); mbar_init(&bars[i][2 + j], 1); mbar_init(&bars[i][4 + j], 128); mbar_init(&bars[i][6 + j], 128);
       }
-#pragma unroll
-    for (int i = 0; i < MAX_KBOX; ++i) mbar_init(&bar_k[i], 1);
+    mbar_init(&bar_k, 1);
     mbar_init(&bar_v, 1);
     mbar_fence_init();
     if (a.kv_tma) {
       // the whole key window of every view is one strided box: 2 instructions instead of 16 B per thread
       const int X = win / a.k_ny, Y = win - X * a.k_ny;
       const int c1 = p.kvmap.grid ? Y : Y * p.kvmap.w2, c2 = p.kvmap.grid ? X : X * p.kvmap.w1;
-      const uint32_t box_bytes = (uint32_t)(a.kv_box_views * p.kvmap.w1 * p.kvmap.w2) * 64u;
-      for (int i = 0; i < a.kv_nbox; ++i) {          // K: box i = views [i * kv_box_views, ...), landing at its own key offset
-        mbar_arrive_expect_tx(&bar_k[i], box_bytes);
-        tma_load_4d(sK + (size_t)i * box_bytes, &a.tmK, &bar_k[i], head * DH, c1, c2, b * a.kv_vt + view0 + i * a.kv_box_views);
-      }
+      mbar_arrive_expect_tx(&bar_k, (uint32_t)a.Lk * 64u);
+      tma_load_4d(sK, &a.tmK, &bar_k, head * DH, c1, c2, b * a.kv_vt + view0);
       mbar_arrive_expect_tx(&bar_v, (uint32_t)a.Lk * 64u);
-      for (int i = 0; i < a.kv_nbox; ++i)
-        tma_load_4d(sV + (size_t)i * box_bytes, &a.tmV, &bar_v, head * DH, c1, c2, b * a.kv_vt + view0 + i * a.kv_box_views);
+      tma_load_4d(sV, &a.tmV, &bar_v, head * DH, c1, c2, b * a.kv_vt + view0);
     }
   }
   if (warp == 0) {
@@ -1042,8 +1033,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
             "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
             ::"r"(d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(acc) : "memory");
       };
-      int kbox_ready = a.kv_tma ? 0 : MAX_KBOX;                    // K boxes known to have landed
-      const int keys_per_box = a.kv_box_views * p.kvmap.w1 * p.kvmap.w2;
+      if (a.kv_tma) mbar_wait(&bar_k, 0);
       int gq = 0, Pq = 0, kq = 0;          // next S chunk to issue: flat index, pass, chunk in pass
       auto next_qk = [&]() {                // S(gq) = Q(Pq) K(chunk)^T
         if (kq == 0) {
@@ -1051,15 +1041,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           tc_fence_after_sync();
         }
         const uint32_t qa = q_addr + (Pq & 1) * (SQ_BYTES / 16);
-        const int chunk = c_first + kq * c_step;
-        if (kbox_ready < a.kv_nbox) {                                // the K boxes covering this chunk's keys
-          int last_key = chunk * CH3 + CH3 - 1;
-          if (last_key >= a.Lk) last_key = a.Lk - 1;
-          const int need = last_key / keys_per_box + 1;
-          while (kbox_ready < need) { mbar_wait(&bar_k[kbox_ready], 0); ++kbox_ready; }
-          tc_fence_after_sync();
-        }
-        const uint32_t kb = k_addr + chunk * (CH3 * 64 / 16);
+        const uint32_t kb = k_addr + (c_first + kq * c_step) * (CH3 * 64 / 16);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
@@ -1514,8 +1496,6 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   a.bias_ld = a.kv_vt * km.w1 * km.w2;
   a.q_dbuf = 0;
   a.kv_tma = 0;
-  a.kv_box_views = km.views;
-  a.kv_nbox = 1;
   a.dbg = 0;
 #ifdef COBEVT_DEBUG_KNOBS
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("COBEVT_ATTN_DEBUG"); dbg = e ? atoi(e) : 0; } a.dbg = dbg; }
@@ -1584,19 +1564,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
           const cuuint64_t dims[4] = {(cuuint64_t)a.C, (cuuint64_t)km.Wv, (cuuint64_t)km.Hv, (cuuint64_t)p->B * a.kv_vt};
           const cuuint64_t strides[3] = {(cuuint64_t)a.p.kv_stride * 2, (cuuint64_t)km.Wv * a.p.kv_stride * 2,
                                          (cuuint64_t)km.Hv * km.Wv * a.p.kv_stride * 2};
-          // K boxes: the fewest views whose keys fill whole 128-byte lines (TMA destination alignment) and at least one
-          // 64-key chunk; at most 8 boxes
-          int bv = km.views;
-          if (COBEVT_KV_BOXES) {
-            for (int c = 1; c < km.views; ++c) {
-              if (km.views % c) continue;
-              const int keys = c * km.w1 * km.w2;
-              if ((keys * 64) % 128 == 0 && keys >= CH3 && km.views / c <= 8) { bv = c; break; }
-            }
-          }
-          a.kv_box_views = bv;
-          a.kv_nbox = km.views / bv;
-          const cuuint32_t box[4] = {DH, (cuuint32_t)span_w, (cuuint32_t)span_h, (cuuint32_t)bv};
+          const cuuint32_t box[4] = {DH, (cuuint32_t)span_w, (cuuint32_t)span_h, (cuuint32_t)km.views};
           const cuuint32_t es[4] = {1, (cuuint32_t)sy, (cuuint32_t)sx, 1};
           const CUresult r1 = enc(&a.tmK, dt, 4, const_cast<void*>(p->k), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                   CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -2,9 +2,9 @@
 on identical seeded weights and inputs.
 
 Tolerance: the kernels store activations as fp16 (fp32 accumulation); the bar is
-max|err| <= tol * max|ref| with tol stated per test (1e-3 is the north_star figure for a
-single fp16 op; whole-model chains of ~60 fp16 roundings are held to 1e-2 and the measured
-value is printed).
+max|err| <= tol * max|ref|.  Whole-model bound 4.5e-3 = this repo's measured error (1.9e-3 .. 2.9e-3) x 1.5,
+below what the unmodified reference itself moves under fp16 autocast (2.3e-3 .. 5.4e-3,
+tests/golden/autocast_error.json); see tests/test_golden.py.
 """
 import copy
 
@@ -43,7 +43,7 @@ def test_corpbevt_small_vs_oracle(record_len, n_cams):
         assert out[k].shape == ref[k].shape
     e = relerr(out["dynamic_seg"], ref["dynamic_seg"])
     print("corpbevt small rel err", e)
-    assert e < 1e-2, e
+    assert e < 4.5e-3, e
     assert out["static_seg"].abs().max().item() == 0.0
 
 
@@ -59,7 +59,7 @@ def test_fax_fused_small_vs_oracle():
         out = m.cuda()(synth.to_device(batch, "cuda"))
     e = relerr(out["dynamic_seg"], ref["dynamic_seg"])
     print("fax fused small rel err", e)
-    assert e < 1e-2, e
+    assert e < 4.5e-3, e
 
 
 def test_full_size_batch_independence():
