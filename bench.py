@@ -308,6 +308,26 @@ def extra_configs(dev):
                                                            "cams": 6, "bev": 256, "dtype": "bf16"}
         except Exception as ex:   # noqa: BLE001
             out["C2_error"] = repr(ex)[:300]
+        # ---- the headline workload at other batch sizes (the small stage-1/2, FuseBEVT and decoder launches are
+        #      latency-bound at 4 samples per step: a serving deployment can trade step latency for throughput) ----
+        try:
+            from cobevt_b200.parallel import ShardedCorpBEVT
+            cfgn = configs.north_star()
+            mn = cb.CorpBEVT(copy.deepcopy(cfgn)).eval()
+            mn.load_state_dict(synth.synth_state_dict(mn, seed=0))
+            mn = mn.to(dev)
+            sweep = {}
+            for S in (1, 2, 8):
+                batch = synth.to_device(synth.synth_batch(dict(cfgn, max_cav=5), record_len=(5,) * S, n_cams=CAMS, seed=1), dev)
+                sh = ShardedCorpBEVT(mn, 0, 1, graphs=True)
+                ms = _time_fn(lambda: sh(batch, [5] * S, batch["transformation_matrix"]), iters=10)
+                sweep[str(S)] = {"samples_per_s": S * 1e3 / ms, "ms_per_step": ms}
+                del sh, batch
+            out["north_star_samples_per_step_sweep"] = sweep
+            del mn
+            torch.cuda.empty_cache()
+        except Exception as ex:   # noqa: BLE001
+            out["sweep_error"] = repr(ex)[:300]
         # ---- C3 / C4 geometry ------------------------------------------------------------------------------
         try:
             cfg = configs.native_opv2v()

@@ -80,6 +80,8 @@ def lib():
         L.cobevt_token_mlp_fwd.argtypes = [ctypes.POINTER(MlpParams), c_vp]
         L.cobevt_window_attn_fwd.restype = ctypes.c_int
         L.cobevt_window_attn_fwd.argtypes = [ctypes.POINTER(AttnParams), c_vp]
+        L.cobevt_attn_workspace_bytes.restype = ctypes.c_int64
+        L.cobevt_attn_workspace_bytes.argtypes = [ctypes.POINTER(AttnParams)]
         L.cobevt_attn_resident_keys.restype = ctypes.c_int32
         L.cobevt_attn_resident_keys.argtypes = []
         L.cobevt_attn_merge.restype = ctypes.c_int
@@ -127,5 +129,5 @@ def check(rc, what):
 
 EXPORTED_SYMBOLS = [
     "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
-    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_token_mlp_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys",
+    "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_token_mlp_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys", "cobevt_attn_workspace_bytes",
 ] + list(_ELTWISE_SIGS)

@@ -1627,6 +1627,16 @@ extern "C" int cobevt_attn_merge(const float* part, int32_t segments, int64_t se
   return cobevt::check_launch("attn_merge_kernel");
 }
 
+extern "C" int64_t cobevt_attn_workspace_bytes(const CobevtAttnParams* p) {
+  // key-segment mode scratch (`part`): kv_segments x B x windows x heads x Lq x 36 floats; 0 for a single resident pass
+  if (!p || p->kv_segments <= 1) return 0;
+  const CobevtTokenMap& qm = p->qmap;
+  if (qm.w1 <= 0 || qm.w2 <= 0 || qm.H % qm.w1 || qm.W % qm.w2) return -1;
+  const int64_t n_win = (int64_t)(qm.H / qm.w1) * (qm.W / qm.w2);
+  const int64_t Lq = (int64_t)qm.views * qm.w1 * qm.w2;
+  return (int64_t)p->kv_segments * p->B * n_win * p->heads * Lq * 36 * (int64_t)sizeof(float);
+}
+
 extern "C" int32_t cobevt_attn_resident_keys(void) {
   return ((227 * 1024 - v3_fixed_smem()) / (128 + 4)) / CH3 * CH3;
 }

@@ -308,13 +308,15 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
         while kvmap.views % vps:                                 # equal segments -> ONE launch covers them all
             vps -= 1
         nseg = kvmap.views // vps
-        part = torch.empty((nseg, B, n_win, heads, lq, 36), dtype=torch.float32, device=q.device)
+        ps = AttnParams.from_buffer_copy(p)
+        ps.kvmap = token_map(vps, kvmap.H, kvmap.W, kvmap.w1, kvmap.w2, bool(kvmap.grid))
+        ps.out = None
+        ps.kv_view0, ps.kv_views_total, ps.kv_segments = 0, kvmap.views, nseg
+        nbytes = int(_lib.lib().cobevt_attn_workspace_bytes(ctypes.byref(ps)))      # the library sizes its own scratch
+        assert nbytes == nseg * B * n_win * heads * lq * 36 * 4, nbytes
+        part = torch.empty((nseg, nbytes // (4 * nseg)), dtype=torch.float32, device=q.device)
         with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32, label + f" segs={nseg}"):
-            ps = AttnParams.from_buffer_copy(p)
-            ps.kvmap = token_map(vps, kvmap.H, kvmap.W, kvmap.w1, kvmap.w2, bool(kvmap.grid))
-            ps.out = None
             ps.part = ctypes.c_void_p(part.data_ptr())
-            ps.kv_view0, ps.kv_views_total, ps.kv_segments = 0, kvmap.views, nseg
             ps.part_segment_stride = part[0].numel()
             _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(ps), _stream()), "cobevt_window_attn_fwd")
             _lib.check(_lib.lib().cobevt_attn_merge(ctypes.c_void_p(part.data_ptr()), nseg, part[0].numel(), _ptr(out),

@@ -151,6 +151,10 @@ typedef struct {
 
 int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);
 
+/* Bytes of the caller-owned fp32 scratch `part` a key-segment call needs (kv_segments > 1), 0 otherwise, < 0 on a bad
+ * query map: the library never allocates, callers size the workspace with this query. */
+int64_t cobevt_attn_workspace_bytes(const CobevtAttnParams* p);
+
 /* Largest number of keys one call keeps resident per window on the four-warpgroup kernel (longer multi-view
  * windows: key-segment mode above). */
 int32_t cobevt_attn_resident_keys(void);
