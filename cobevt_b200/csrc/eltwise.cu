@@ -107,88 +107,145 @@ __global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restri
 // left): the 7x7/s2 stem then needs no bounds checks and its taps start on 16-byte boundaries.
 __global__ void pack_rgb4_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
                                      int Hp, int Wp, int pt, int pl, int nchw, float3 mean, float3 istd, int bf16) {
+  // two output pixels (one 16-byte store) per thread, Wp is even: twice the bytes in flight of the one-pixel version
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (int64_t)N * Hp * Wp) return;
-  const int xp = (int)(i % Wp);
-  const int yp = (int)((i / Wp) % Hp);
-  const int n = (int)(i / ((int64_t)Wp * Hp));
-  const int ys = yp - pt, xs = xp - pl;
-  uint2 u = make_uint2(0u, 0u);
-  if (ys >= 0 && ys < H && xs >= 0 && xs < W) {
-    float r, g, b;
-    if (nchw) {     // (N,3,H,W) planes (nuScenes batch['image'])
-      const int64_t hw = (int64_t)H * W, o = (int64_t)n * 3 * hw + (int64_t)ys * W + xs;
-      r = x[o]; g = x[o + hw]; b = x[o + 2 * hw];
-    } else {
-      const float* s = x + (((int64_t)n * H + ys) * W + xs) * 3;
-      r = s[0]; g = s[1]; b = s[2];
-    }
-    u.x = pk2((r - mean.x) * istd.x, (g - mean.y) * istd.y, bf16);
-    u.y = pk2((b - mean.z) * istd.z, 0.f, bf16);
-  }
-  *reinterpret_cast<uint2*>(y + i * 4) = u;
-}
-
-// ------------------------------------------------------------------ maxpool 3x3 s2 p1
-__global__ void maxpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int C,
-                               int OH, int OW, int bf16) {
-  const int cg = C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t total = (int64_t)N * OH * OW * cg;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % cg);
-  int64_t t = idx / cg;
-  const int ox = (int)(t % OW); t /= OW;
-  const int oy = (int)(t % OH);
-  const int n = (int)(t / OH);
-  float m[8];
+  const int Wh = Wp >> 1;
+  if (i >= (int64_t)N * Hp * Wh) return;
+  const int xp = (int)(i % Wh) * 2;
+  const int yp = (int)((i / Wh) % Hp);
+  const int n = (int)(i / ((int64_t)Wh * Hp));
+  const int ys = yp - pt;
+  uint32_t o[4] = {0u, 0u, 0u, 0u};
+  if (ys >= 0 && ys < H) {
 #pragma unroll
-  for (int j = 0; j < 8; ++j) m[j] = -INFINITY;
-  for (int ky = 0; ky < 3; ++ky) {
-    const int iy = oy * 2 - 1 + ky;
-    if (iy < 0 || iy >= H) continue;
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ix = ox * 2 - 1 + kx;
-      if (ix < 0 || ix >= W) continue;
-      const uint4 u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + iy) * W + ix) * C + c8 * 8);
-      const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = up2(w4[j], bf16);
-        m[2 * j] = fmaxf(m[2 * j], f.x);
-        m[2 * j + 1] = fmaxf(m[2 * j + 1], f.y);
+    for (int k = 0; k < 2; ++k) {
+      const int xs = xp + k - pl;
+      if (xs >= 0 && xs < W) {
+        float r, g, b;
+        if (nchw) {     // (N,3,H,W) planes (nuScenes batch['image'])
+          const int64_t hw = (int64_t)H * W, off = (int64_t)n * 3 * hw + (int64_t)ys * W + xs;
+          r = x[off]; g = x[off + hw]; b = x[off + 2 * hw];
+        } else {
+          const float* s = x + (((int64_t)n * H + ys) * W + xs) * 3;
+          r = s[0]; g = s[1]; b = s[2];
+        }
+        o[2 * k] = pk2((r - mean.x) * istd.x, (g - mean.y) * istd.y, bf16);
+        o[2 * k + 1] = pk2((b - mean.z) * istd.z, 0.f, bf16);
       }
     }
   }
-  uint4 o;
-  o.x = pk2(m[0], m[1], bf16); o.y = pk2(m[2], m[3], bf16); o.z = pk2(m[4], m[5], bf16); o.w = pk2(m[6], m[7], bf16);
-  *reinterpret_cast<uint4*>(y + (((int64_t)n * OH + oy) * OW + ox) * C + c8 * 8) = o;
+  *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// ------------------------------------------------------------------ maxpool 3x3 s2 p1
+// Two horizontally adjacent outputs per thread (their 3x3 windows share a column: 15 loads instead of 18), every load
+// issued up front with clamped coordinates (no control flow between them: 240 bytes in flight per thread), the
+// maximum taken in the packed 16-bit domain (max is exact there), -inf for the padding.
+template <bool BF16>
+__device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b) {
+  if constexpr (BF16) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  } else {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+}
+template <bool BF16>
+__global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H,
+                                                      int W, int C, int OH, int OW) {
+  const int cg = C / 8;
+  const int OWp = (OW + 1) >> 1;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * OH * OWp * cg) return;
+  const int c8 = (int)(idx % cg);
+  int64_t t = idx / cg;
+  const int oxp = (int)(t % OWp); t /= OWp;
+  const int oy = (int)(t % OH);
+  const int n = (int)(t / OH);
+  const int ox0 = oxp * 2;
+  constexpr uint32_t NINF = BF16 ? 0xFF80FF80u : 0xFC00FC00u;
+  uint4 v[3][5];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - 1 + ky;
+    const bool vy = iy >= 0 && iy < H;
+    const int iyc = min(max(iy, 0), H - 1);
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const int ix = ox0 * 2 - 1 + kx;
+      const bool ok = vy && ix >= 0 && ix < W;
+      const int ixc = min(max(ix, 0), W - 1);
+      const uint4 u = *reinterpret_cast<const uint4*>(x + (((int64_t)n * H + iyc) * W + ixc) * C + c8 * 8);
+      v[ky][kx] = ok ? u : make_uint4(NINF, NINF, NINF, NINF);
+    }
+  }
+  auto mx4 = [](uint4 a, uint4 b) {
+    return make_uint4(max2_16<BF16>(a.x, b.x), max2_16<BF16>(a.y, b.y), max2_16<BF16>(a.z, b.z), max2_16<BF16>(a.w, b.w));
+  };
+  uint4 col[5];
+#pragma unroll
+  for (int kx = 0; kx < 5; ++kx) col[kx] = mx4(mx4(v[0][kx], v[1][kx]), v[2][kx]);
+  const uint4 o0 = mx4(mx4(col[0], col[1]), col[2]);
+  const uint4 o1 = mx4(mx4(col[2], col[3]), col[4]);
+  uint16_t* yp = y + (((int64_t)n * OH + oy) * OW + ox0) * C + c8 * 8;
+  *reinterpret_cast<uint4*>(yp) = o0;
+  if (ox0 + 1 < OW) *reinterpret_cast<uint4*>(yp + C) = o1;
 }
 
 // ------------------------------------------------------------------ y = relu(x*s + b), two affine sets
-__global__ void bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ sa, const float* __restrict__ ba,
-                                uint16_t* __restrict__ ya, const float* __restrict__ sb, const float* __restrict__ bb,
-                                uint16_t* __restrict__ yb, int64_t rows, int C, int bf16) {
+// Four 16-byte vectors per thread, one block-stride apart: the four loads are in flight together (a streaming kernel
+// with 16 bytes per thread in flight sits at ~4 TB/s).  SAME_CG: 256 % (C / 8) == 0, so all four vectors of a thread
+// share one channel group and the scale / shift vectors are read once per thread; otherwise (56 / 112-channel
+// EfficientNet features) they are read per vector.
+template <bool SAME_CG>
+__global__ void __launch_bounds__(256) bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ sa,
+                                const float* __restrict__ ba, uint16_t* __restrict__ ya, const float* __restrict__ sb,
+                                const float* __restrict__ bb, uint16_t* __restrict__ yb, int64_t nvec, int C, int bf16) {
+  constexpr int VPT = 4;
   const int cg = C / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * cg) return;
-  const int c0 = (int)(idx % cg) * 8;
-  const uint4 u = *reinterpret_cast<const uint4*>(x + idx * 8);
-  const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
-  float v[8];
+  const int64_t base = (int64_t)blockIdx.x * (256 * VPT) + threadIdx.x;
+  uint4 u[VPT];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) { const float2 f = up2(w4[j], bf16); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
-  float o[8];
+  for (int i = 0; i < VPT; ++i) {
+    const int64_t idx = base + (int64_t)i * 256;
+    u[i] = idx < nvec ? *reinterpret_cast<const uint4*>(x + idx * 8) : make_uint4(0, 0, 0, 0);
+  }
+  float s0[8], t0[8], s1[8], t1[8];
+  auto load_affine = [&](int c0) {
+    *reinterpret_cast<float4*>(s0) = *reinterpret_cast<const float4*>(sa + c0);
+    *reinterpret_cast<float4*>(s0 + 4) = *reinterpret_cast<const float4*>(sa + c0 + 4);
+    *reinterpret_cast<float4*>(t0) = *reinterpret_cast<const float4*>(ba + c0);
+    *reinterpret_cast<float4*>(t0 + 4) = *reinterpret_cast<const float4*>(ba + c0 + 4);
+    if (yb) {
+      *reinterpret_cast<float4*>(s1) = *reinterpret_cast<const float4*>(sb + c0);
+      *reinterpret_cast<float4*>(s1 + 4) = *reinterpret_cast<const float4*>(sb + c0 + 4);
+      *reinterpret_cast<float4*>(t1) = *reinterpret_cast<const float4*>(bb + c0);
+      *reinterpret_cast<float4*>(t1 + 4) = *reinterpret_cast<const float4*>(bb + c0 + 4);
+    }
+  };
+  if (SAME_CG) load_affine((int)(base % cg) * 8);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], sa[c0 + j], ba[c0 + j]), 0.f);
-  uint4 w;
-  w.x = pk2(o[0], o[1], bf16); w.y = pk2(o[2], o[3], bf16); w.z = pk2(o[4], o[5], bf16); w.w = pk2(o[6], o[7], bf16);
-  *reinterpret_cast<uint4*>(ya + idx * 8) = w;
-  if (yb) {
+  for (int i = 0; i < VPT; ++i) {
+    const int64_t idx = base + (int64_t)i * 256;
+    if (idx >= nvec) continue;
+    if (!SAME_CG) load_affine((int)(idx % cg) * 8);
+    const uint32_t w4[4] = {u[i].x, u[i].y, u[i].z, u[i].w};
+    float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], sb[c0 + j], bb[c0 + j]), 0.f);
+    for (int j = 0; j < 4; ++j) { const float2 f = up2(w4[j], bf16); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], s0[j], t0[j]), 0.f);
+    uint4 w;
     w.x = pk2(o[0], o[1], bf16); w.y = pk2(o[2], o[3], bf16); w.z = pk2(o[4], o[5], bf16); w.w = pk2(o[6], o[7], bf16);
-    *reinterpret_cast<uint4*>(yb + idx * 8) = w;
+    *reinterpret_cast<uint4*>(ya + idx * 8) = w;
+    if (yb) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaxf(fmaf(v[j], s1[j], t1[j]), 0.f);
+      w.x = pk2(o[0], o[1], bf16); w.y = pk2(o[2], o[3], bf16); w.z = pk2(o[4], o[5], bf16); w.w = pk2(o[6], o[7], bf16);
+      *reinterpret_cast<uint4*>(yb + idx * 8) = w;
+    }
   }
 }
 
@@ -786,8 +843,8 @@ extern "C" int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t d
 extern "C" int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32_t H, int32_t W, int32_t Hp, int32_t Wp,
                                         int32_t pad_top, int32_t pad_left, int32_t src_nchw, const float* mean3,
                                         const float* std3, int32_t dtype, void* stream) {
-  if (!x || !y || N <= 0 || Hp < H + pad_top || Wp < W + pad_left) return fail(COBEVT_ERR_SHAPE, "pack_rgb4_padded: bad args");
-  const int64_t total = (int64_t)N * Hp * Wp;
+  if (!x || !y || N <= 0 || Hp < H + pad_top || Wp < W + pad_left || (Wp & 1)) return fail(COBEVT_ERR_SHAPE, "pack_rgb4_padded: bad args (Wp must be even)");
+  const int64_t total = (int64_t)N * Hp * (Wp / 2);
   // mean3 / std3 are HOST pointers (3 floats each) or NULL: the Normalize of encoder_pyramid_axial.py:41-49
   float3 mean = make_float3(0.f, 0.f, 0.f), istd = make_float3(1.f, 1.f, 1.f);
   if (mean3 && std3) { mean = make_float3(mean3[0], mean3[1], mean3[2]); istd = make_float3(1.f / std3[0], 1.f / std3[1], 1.f / std3[2]); }
@@ -799,16 +856,22 @@ extern "C" int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32
                                          int32_t dtype, void* stream) {
   if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "maxpool: bad args");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)N * OH * OW * (C / 8);
-  maxpool_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW, dtype);
+  const int64_t total = (int64_t)N * OH * ((OW + 1) / 2) * (C / 8);
+  if (dtype == COBEVT_BF16) maxpool_kernel<true><<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
+  else maxpool_kernel<false><<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
   return cobevt::check_launch("maxpool");
 }
 
 extern "C" int cobevt_bn_relu2(const void* x, const float* sa, const float* ba, void* ya, const float* sb,
                                 const float* bb, void* yb, int64_t rows, int32_t C, int32_t dtype, void* stream) {
   if (!x || !sa || !ba || !ya || C % 8 || (yb && (!sb || !bb))) return fail(COBEVT_ERR_SHAPE, "bn_relu2: bad args");
-  bn_relu2_kernel<<<blocks_for(rows * (C / 8), 256), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
-                                                                         (uint16_t*)yb, rows, C, dtype);
+  const int64_t nvec = rows * (C / 8);
+  if (256 % (C / 8) == 0)
+    bn_relu2_kernel<true><<<blocks_for(nvec, 1024), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
+                                                                         (uint16_t*)yb, nvec, C, dtype);
+  else
+    bn_relu2_kernel<false><<<blocks_for(nvec, 1024), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
+                                                                          (uint16_t*)yb, nvec, C, dtype);
   return cobevt::check_launch("bn_relu2");
 }
 

@@ -349,3 +349,30 @@ def test_token_mlp_fused_vs_two_gemms_and_fp32(M, affine, dt):
     assert relerr(yln, refln) < tol, relerr(yln, refln)
     _, only_ln = ops.token_mlp(x, fused, res, want16=False, ln_gamma=gamma, ln_beta=beta)
     assert torch.equal(only_ln, yln)
+
+
+# --------------------------------------------------------------------------- streaming kernels rewritten in round 2
+@pytest.mark.parametrize("shape", [(2, 112, 240, 64), (1, 33, 17, 64), (3, 8, 9, 128)])
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+def test_maxpool_exact(shape, dt):
+    """3x3 / stride 2 / pad 1 max-pool on NHWC (resnet_ms.py:71): exact (max commutes with the 16-bit rounding)."""
+    from cobevt_b200 import ops
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g).to(dt).cuda()
+    y = ops.maxpool3x3s2(x)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(dt)
+    assert y.shape == ref.shape
+    assert torch.equal(y, ref)
+
+
+@pytest.mark.parametrize("C", [64, 128, 256, 56, 112])
+def test_bn_relu2(C):
+    from cobevt_b200 import ops
+    g = torch.Generator().manual_seed(C)
+    x = torch.randn(3, 13, 11, C, generator=g).half().cuda()
+    sa, ba, sb, bb = [torch.randn(C, generator=g).cuda() for _ in range(4)]
+    ya, yb = ops.bn_relu2(x, sa, ba, sb, bb)
+    assert relerr(ya, F.relu(x.float() * sa + ba)) < 1e-3
+    assert relerr(yb, F.relu(x.float() * sb + bb)) < 1e-3
+    only, none = ops.bn_relu2(x, sa, ba)
+    assert none is None and torch.equal(only, ya)
