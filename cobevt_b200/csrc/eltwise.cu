@@ -523,6 +523,17 @@ __global__ void __launch_bounds__(256) bev_query_grouped_kernel(const uint16_t* 
     wb1[i] = w_bev[ch * 2 + 1];
     ce[i] = b_bev[ch] - (w_cam[ch * 4] * c0 + w_cam[ch * 4 + 1] * c1 + w_cam[ch * 4 + 2] * c2 + w_cam[ch * 4 + 3] * c3);
   }
+  // e(cell) = wb0 wx + wb1 wy + ce is affine in the cell's world coordinates, so its squared norm is a quadratic form
+  // with six per-view constants: the L2 normalisation needs no per-cell reduction; the LayerNorm statistics of
+  // y = x + e / (|e| + 1e-7) then come from ONE reduction round of (sum y, sum y^2) instead of three dependent ones.
+  float qa = 0.f, qb = 0.f, qc = 0.f, qd = 0.f, qe = 0.f, qf = 0.f;
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) {
+    qa = fmaf(wb0[i], wb0[i], qa); qb = fmaf(wb1[i], wb1[i], qb); qc = fmaf(ce[i], ce[i], qc);
+    qd = fmaf(wb0[i], wb1[i], qd); qe = fmaf(wb0[i], ce[i], qe); qf = fmaf(wb1[i], ce[i], qf);
+  }
+  qa = group_sum<LPC>(qa); qb = group_sum<LPC>(qb); qc = group_sum<LPC>(qc);
+  qd = 2.0f * group_sum<LPC>(qd); qe = 2.0f * group_sum<LPC>(qe); qf = 2.0f * group_sum<LPC>(qf);
   const int base = blockIdx.x * cpb;
   constexpr float invC = 1.0f / (float)C;
   // the loads of the next cell are issued before the reductions of the current one (register prefetch)
@@ -549,33 +560,28 @@ __global__ void __launch_bounds__(256) bev_query_grouped_kernel(const uint16_t* 
       xv[q * 8 + 4] = c.x; xv[q * 8 + 5] = c.y; xv[q * 8 + 6] = d.x; xv[q * 8 + 7] = d.y;
     }
     if (cc + 8 * CPW < cpb) fetch(cc + 8 * CPW);
-    // packed fp32 pairs: 4 issue slots per element for the whole chain
-    float ss0 = 0.f, ss1 = 0.f;
+    const float ss = fmaxf(fmaf(wx, fmaf(qa, wx, fmaf(qd, wy, qe)), fmaf(wy, fmaf(qb, wy, qf), qc)), 0.f);
+    const float inv = __fdividef(1.0f, sqrtf(ss) + 1e-7f);
+    float s10 = 0.f, s11 = 0.f, s20 = 0.f, s21 = 0.f;
 #pragma unroll
     for (int i = 0; i < CPL; i += 2) {
       sm100::ffma2(e[i], e[i + 1], wb1[i], wb1[i + 1], wy, wy, ce[i], ce[i + 1]);
       sm100::ffma2(e[i], e[i + 1], wb0[i], wb0[i + 1], wx, wx, e[i], e[i + 1]);
-      sm100::ffma2(ss0, ss1, e[i], e[i + 1], e[i], e[i + 1], ss0, ss1);
-    }
-    const float ss = group_sum<LPC>(ss0 + ss1);
-    const float inv = __fdividef(1.0f, sqrtf(ss) + 1e-7f);
-    float s10 = 0.f, s11 = 0.f;
-#pragma unroll
-    for (int i = 0; i < CPL; i += 2) {
-      sm100::ffma2(e[i], e[i + 1], e[i], e[i + 1], inv, inv, xv[i], xv[i + 1]);
+      sm100::ffma2(e[i], e[i + 1], e[i], e[i + 1], inv, inv, xv[i], xv[i + 1]);          // y = x + e / |e|
       sm100::fadd2(s10, s11, s10, s11, e[i], e[i + 1]);
-    }
-    const float mean = group_sum<LPC>(s10 + s11) * invC;
-    const float nmean = -mean;
-    float s20 = 0.f, s21 = 0.f;
-#pragma unroll
-    for (int i = 0; i < CPL; i += 2) {
-      sm100::fadd2(e[i], e[i + 1], e[i], e[i + 1], nmean, nmean);
       sm100::ffma2(s20, s21, e[i], e[i + 1], e[i], e[i + 1], s20, s21);
     }
-    const float rstd = rsqrtf(group_sum<LPC>(s20 + s21) * invC + eps);
+    float s1 = s10 + s11, s2 = s20 + s21;
 #pragma unroll
-    for (int i = 0; i < CPL; i += 2) sm100::fmul2(e[i], e[i + 1], e[i], e[i + 1], rstd, rstd);
+    for (int o = LPC / 2; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    const float mean = s1 * invC;
+    const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * invC), 0.f) + eps);
+    const float shift = -mean * rstd;
+#pragma unroll
+    for (int i = 0; i < CPL; i += 2) sm100::ffma2(e[i], e[i + 1], e[i], e[i + 1], rstd, rstd, shift, shift);
     if (cell < P) store_vec<CPL, LPC>(out + ((int64_t)v * P + cell) * C, grp, bf16, e);
   }
 }
