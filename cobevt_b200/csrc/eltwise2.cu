@@ -4,6 +4,7 @@
 // the squeeze-excite gate, the gate application.  Reference lines are cited per entry point in
 // include/cobevt_b200.h.
 #include "common.h"
+#include "sm100.cuh"
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
@@ -198,6 +199,152 @@ __global__ void scale_channels_kernel(const uint16_t* __restrict__ x, const floa
   *reinterpret_cast<uint4*>(y + idx * 8) = pk8(f, bf16);
 }
 
+// ------------------------------------------------------------------ analytic BEV query projection (stage 0 of SinBEVT)
+// q[b,n,p,:] = W' LN0(x[b,p,:] + e / (|e| + 1e-7)) + b',  e = a wx_p + b_ wy_p + c_{b,n}  (fax_modules.py:370-375,387-390
+// and to_q :189-190, W' / b' = the projection with the LayerNorm affine folded in).  e is AFFINE in the cell's world
+// coordinates, so W' e, |e|^2, mean(e) and mean(x e) are closed forms in (wx, wy) with per-channel / per-cell / per-view
+// constants, and LayerNorm is (y - mu) rstd with mu, rstd scalars per token.  Hence
+//   q = rstd (W'x)[b,p] + rstd inv (A wx + B wy + Cc_{b,n}) + (b' - rstd mu S)
+// needs NO per-token reduction and NO GEMM over the (rows x views x cells) tokens: W'x is computed once per (row, cell) by
+// the GEMM kernel, the per-cell statistics once per row map by row_stats9_kernel, and this kernel is a pure streaming
+// write of q (the 503 MB LayerNorm output of bev_query_kernel and its re-read by the q-projection GEMM disappear).
+// chan_tab: C x 20 fp32 = [a, b_, b_bev, w_cam(4), 0 | A, B, S, b' | Cb, M4(4), 0, 0, 0] with A = W'a, B = W'b_, S = W'1,
+// Cb = W' b_bev, M4 = W' w_cam (five float4 per channel).  stats: rows x 12 fp32 = means over channels of
+// [x, x^2, x a, x b_, x b_bev, x w_cam(4)].
+template <int C>
+__global__ void __launch_bounds__(256) row_stats9_kernel(const uint16_t* __restrict__ x, const float* __restrict__ tab,
+                                                         float* __restrict__ stats, int64_t rows, int bf16) {
+  constexpr int LPT = C / 8;                       // lanes per row (8 channels each)
+  const int lane = threadIdx.x & 31, g = lane % LPT;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPT;
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  if (row < rows) {
+    float f[8];
+    up8(*reinterpret_cast<const uint4*>(x + row * C + g * 8), bf16, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 d0 = *reinterpret_cast<const float4*>(tab + (g * 8 + j) * 20);        // a, b_, b_bev, w_cam0
+      const float4 d1 = *reinterpret_cast<const float4*>(tab + (g * 8 + j) * 20 + 4);    // w_cam1..3, 0
+      const float v = f[j];
+      acc[0] += v; acc[1] = fmaf(v, v, acc[1]);
+      acc[2] = fmaf(v, d0.x, acc[2]); acc[3] = fmaf(v, d0.y, acc[3]); acc[4] = fmaf(v, d0.z, acc[4]);
+      acc[5] = fmaf(v, d0.w, acc[5]); acc[6] = fmaf(v, d1.x, acc[6]); acc[7] = fmaf(v, d1.y, acc[7]); acc[8] = fmaf(v, d1.z, acc[8]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+#pragma unroll
+    for (int o = LPT / 2; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  if (row < rows && g == 0) {
+    float* o = stats + row * 12;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) o[k] = acc[k] * (1.0f / C);
+  }
+}
+
+// One token = LPT lanes (8 channels each).  The per-(token, view) scalars (|e|, mean, variance) are computed by lane
+// v of the token for view v -- all views at once instead of every lane repeating every view -- and broadcast with
+// three shuffles; the channel math runs on packed fp32 pairs.  Measured 189 us for the 503 MB of the north_star stage 0
+// (2.7 TB/s: pure-write streams on this part level off near 3 TB/s; a register-prefetch / 3-blocks-per-SM variant
+// was slower, 199 us).
+template <int C>
+__global__ void __launch_bounds__(256) bev_q_kernel(const float* __restrict__ qx, int64_t x_rows, const float* __restrict__ stats,
+                                                    const float* __restrict__ world, const float* __restrict__ tab,
+                                                    const float* __restrict__ E_inv, uint16_t* __restrict__ out, int n, int P,
+                                                    float qa, float qb, float qd, float ma, float mb, float eps, int bf16, int cpb) {
+  constexpr int LPT = C / 8, TPB = 256 / LPT;      // lanes per token, tokens per block iteration
+  constexpr int MAXV = 8;
+  __shared__ __align__(16) float sCc[MAXV][C];     // Cc_{b,v} = Cb - M4 t_v
+  __shared__ __align__(16) float sV[MAXV][8];      // per view: qc, qe, qf, mc, t0..t3
+  const int b = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = tid % LPT, tok = tid / LPT;
+  // ---- per-view constants of this agent row ------------------------------------------------------------
+  for (int v = warp; v < MAXV; v += 8) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    if (v < n) {
+      const float* Ei = E_inv + ((int64_t)b * n + v) * 16;
+      t0 = Ei[3]; t1 = Ei[7]; t2 = Ei[11]; t3 = Ei[15];
+    }
+    float qc = 0.f, qe = 0.f, qf = 0.f, mc = 0.f;
+    for (int ch = lane; ch < C; ch += 32) {
+      const float4 d0 = *reinterpret_cast<const float4*>(tab + ch * 20), d1 = *reinterpret_cast<const float4*>(tab + ch * 20 + 4);
+      const float4 c0 = *reinterpret_cast<const float4*>(tab + ch * 20 + 12), c1 = *reinterpret_cast<const float4*>(tab + ch * 20 + 16);
+      const float c = d0.z - (d0.w * t0 + d1.x * t1 + d1.y * t2 + d1.z * t3);
+      qc = fmaf(c, c, qc); qe = fmaf(d0.x, c, qe); qf = fmaf(d0.y, c, qf); mc += c;
+      sCc[v][ch] = c0.x - (c0.y * t0 + c0.z * t1 + c0.w * t2 + c1.x * t3);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      qc += __shfl_xor_sync(0xffffffffu, qc, o); qe += __shfl_xor_sync(0xffffffffu, qe, o);
+      qf += __shfl_xor_sync(0xffffffffu, qf, o); mc += __shfl_xor_sync(0xffffffffu, mc, o);
+    }
+    if (lane == 0) {
+      sV[v][0] = qc; sV[v][1] = 2.0f * qe; sV[v][2] = 2.0f * qf; sV[v][3] = mc * (1.0f / C);
+      sV[v][4] = t0; sV[v][5] = t1; sV[v][6] = t2; sV[v][7] = t3;
+    }
+  }
+  float A8[8], B8[8], S8[8], Q8[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 q = *reinterpret_cast<const float4*>(tab + (g * 8 + j) * 20 + 8);
+    A8[j] = q.x; B8[j] = q.y; S8[j] = q.z; Q8[j] = q.w;
+  }
+  __syncthreads();
+  // this lane's view (for the scalar stage): lane g of a token handles view g (views >= LPT: see host check)
+  const float4 va = *reinterpret_cast<const float4*>(sV[g < MAXV ? g : 0]), vb = *reinterpret_cast<const float4*>(sV[g < MAXV ? g : 0] + 4);
+  const int64_t xrow0 = (x_rows == (int64_t)P) ? 0 : (int64_t)b * P;      // broadcast prior or per-row map
+  const int base = blockIdx.x * cpb;
+  constexpr float invC = 1.0f / C;
+  const int lane_tok0 = lane - g;                                           // first lane of this token inside the warp
+  for (int cc = tok; cc < cpb; cc += TPB) {
+    const int cellr = base + cc;
+    const bool live = cellr < P;
+    const int cell = live ? cellr : P - 1;                                  // (shuffles below need every lane)
+    const float wx = world[cell], wy = world[P + cell];
+    const float* st = stats + (xrow0 + cell) * 12;
+    const float4 s0 = *reinterpret_cast<const float4*>(st), s1 = *reinterpret_cast<const float4*>(st + 4);
+    const float s8 = st[8];
+    const float* qp = qx + (xrow0 + cell) * C + g * 8;
+    const float4 q0 = *reinterpret_cast<const float4*>(qp), q1 = *reinterpret_cast<const float4*>(qp + 4);
+    const float xq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float lin[8];                                                          // A wx + B wy (view independent)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lin[j] = fmaf(A8[j], wx, B8[j] * wy);
+    // ---- scalars of (cell, view g), by lane g --------------------------------------------------------------
+    float m_rstd, m_k1, m_k2;
+    {
+      const float ss = fmaxf(fmaf(wx, fmaf(qa, wx, fmaf(qd, wy, va.y)), fmaf(wy, fmaf(qb, wy, va.z), va.x)), 0.f);
+      const float inv = __fdividef(1.0f, sqrtf(ss) + 1e-7f);
+      const float mu = fmaf(inv, fmaf(ma, wx, fmaf(mb, wy, va.w)), s0.x);
+      const float xe = fmaf(s0.z, wx, fmaf(s0.w, wy, s1.x)) - (s1.y * vb.x + s1.z * vb.y + s1.w * vb.z + s8 * vb.w);
+      const float ey2 = fmaf(inv * inv, ss * invC, fmaf(2.0f * inv, xe, s0.y));
+      m_rstd = rsqrtf(fmaxf(fmaf(-mu, mu, ey2), 0.f) + eps);
+      m_k1 = m_rstd * inv;
+      m_k2 = -m_rstd * mu;
+    }
+    for (int v = 0; v < n; ++v) {
+      const float rstd = __shfl_sync(0xffffffffu, m_rstd, lane_tok0 + v);
+      const float k1 = __shfl_sync(0xffffffffu, m_k1, lane_tok0 + v);
+      const float k2 = __shfl_sync(0xffffffffu, m_k2, lane_tok0 + v);
+      const float4 c0 = *reinterpret_cast<const float4*>(&sCc[v][g * 8]), c1 = *reinterpret_cast<const float4*>(&sCc[v][g * 8 + 4]);
+      const float cc8[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        float e0, e1, b0, b1;
+        sm100::fadd2(e0, e1, lin[j], lin[j + 1], cc8[j], cc8[j + 1]);
+        sm100::ffma2(b0, b1, S8[j], S8[j + 1], k2, k2, Q8[j], Q8[j + 1]);
+        sm100::ffma2(b0, b1, e0, e1, k1, k1, b0, b1);
+        sm100::ffma2(o[j], o[j + 1], xq[j], xq[j + 1], rstd, rstd, b0, b1);
+      }
+      if (live) *reinterpret_cast<uint4*>(out + (((int64_t)b * n + v) * P + cell) * C + g * 8) = pk8(o, bf16);
+    }
+  }
+}
+
 }  // namespace
 
 using cobevt::fail;
@@ -260,4 +407,33 @@ extern "C" int cobevt_scale_channels(const void* x, const float* gate, void* y, 
   if (!x || !gate || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "scale_channels: bad args");
   scale_channels_kernel<<<blocks_for((int64_t)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>((const uint16_t*)x, gate, (uint16_t*)y, N, HW, C, dtype);
   return cobevt::check_launch("scale_channels");
+}
+
+extern "C" int cobevt_row_stats9(const void* x, const float* chan_tab, float* stats, int64_t rows, int32_t C, int32_t dtype,
+                                 void* stream) {
+  if (!x || !chan_tab || !stats || rows <= 0 || (C != 32 && C != 64 && C != 128)) return fail(COBEVT_ERR_SHAPE, "row_stats9: bad args (C in {32,64,128})");
+  const int64_t threads = rows * (C / 8);
+  if (C == 128) row_stats9_kernel<128><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
+  else if (C == 64) row_stats9_kernel<64><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
+  else row_stats9_kernel<32><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
+  return cobevt::check_launch("row_stats9");
+}
+
+extern "C" int cobevt_bev_q_analytic(const float* qx, int64_t x_rows, const float* stats, const float* world, const float* chan_tab,
+                                     const float* E_inv, void* out, int32_t BL, int32_t n, int32_t P, int32_t C, float qa, float qb,
+                                     float qd, float ma, float mb, float eps, int32_t dtype, void* stream) {
+  if (!qx || !stats || !world || !chan_tab || !E_inv || !out || BL <= 0 || n <= 0 || n > 8 || n > C / 8 || P <= 0 || BL > 65535 ||
+      (C != 32 && C != 64 && C != 128) || (x_rows != P && x_rows != (int64_t)BL * P))
+    return fail(COBEVT_ERR_SHAPE, "bev_q_analytic: bad args (C in {32,64,128}, n <= min(8, C/8), x_rows in {P, BL*P})");
+  // cells per block: ~4 blocks per SM overall, at least one block iteration of tokens
+  int64_t cpb = ((int64_t)P * BL + 148 * 4 - 1) / (148 * 4);
+  const int tpb = 256 / (C / 8);
+  cpb = (cpb + tpb - 1) / tpb * tpb;
+  if (cpb < tpb) cpb = tpb;
+  if (cpb > 4096) cpb = 4096;
+  dim3 grid((unsigned)((P + cpb - 1) / cpb), (unsigned)BL);
+  if (C == 128) bev_q_kernel<128><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  else if (C == 64) bev_q_kernel<64><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  else bev_q_kernel<32><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  return cobevt::check_launch("bev_q_analytic");
 }

@@ -190,6 +190,22 @@ class FaxStagePlan:
             self.world = _dev_f32(world.reshape(2, -1), device)
         self.a1 = CrossAttnPlan(cva.cross_win_attend_1, device, dtype)
         self.a2 = CrossAttnPlan(cva.cross_win_attend_2, device, dtype)
+        if self.bev_flag:
+            # analytic query projection (csrc/eltwise2.cu bev_q_kernel): q = W' LN0(x + e/|e|) + b' with e affine in the
+            # cell's world coordinates -- per-channel constants of W' applied to the embedding vectors, fp32 on the host
+            m = cva.cross_win_attend_1
+            wq, bq = fold_ln_linear(m.to_q[0], m.to_q[1])
+            wq, bq = wq.cpu(), bq.cpu()
+            wb = cva.bev_embed.weight.detach().float().reshape(self.dim, 2).cpu()
+            bb = cva.bev_embed.bias.detach().float().cpu()
+            wc = cva.cam_embed.weight.detach().float().reshape(self.dim, 4).cpu()
+            a_, b_ = wb[:, 0], wb[:, 1]
+            z = torch.zeros_like(a_)
+            tab = torch.stack([a_, b_, bb] + [wc[:, k] for k in range(4)] + [z] + [wq @ a_, wq @ b_, wq.sum(1), bq] +
+                              [wq @ bb] + [wq @ wc[:, k] for k in range(4)] + [z, z, z], dim=1)          # (C, 20)
+            self.q_tab = tab.contiguous().to(device)
+            self.q_consts = (float(a_ @ a_), float(b_ @ b_), float(2 * (a_ @ b_)), float(a_.mean()), float(b_.mean()))
+            self.q_wx = PackedConv(wq, None, device, dtype)
         # both attentions project the same normalised key / value maps: one N=256 GEMM each
         self.k12 = PackedConv(torch.cat([self.a1.wk, self.a2.wk], 0), torch.cat([self.a1.bk, self.a2.bk], 0), device, dtype)
         self.v12 = PackedConv(torch.cat([self.a1.wv, self.a2.wv], 0), torch.cat([self.a1.bv, self.a2.bv], 0), device, dtype)
@@ -229,13 +245,18 @@ class FaxStagePlan:
         wp = w if w % fw == 0 else ((w + fw) // fw) * fw
         padded = (hp, wp) != (h, w)
         # ---- queries ---------------------------------------------------------------------------
-        if self.bev_flag:
-            q_hat = ops.bev_query(x.reshape(-1, d), self.world, self.w_bev, self.b_bev, self.w_cam, E_inv, BL, n, P)
+        if self.bev_flag and d in (32, 64, 128) and n <= min(8, d // 8):
+            q1 = ops.bev_q_analytic(x.reshape(-1, d), self.q_wx, self.q_tab, self.q_consts, self.world, E_inv, BL, n, P)
+            q1 = q1.view(BL, n, H, W, d)
             nq = n
         else:
-            q_hat = x_ln if x_ln is not None else ops.layernorm_rows(x)
-            nq = 1
-        q1 = ops.linear_tokens(q_hat.reshape(-1, d), self.a1.q)[0].view(BL, nq, H, W, d)
+            if self.bev_flag:
+                q_hat = ops.bev_query(x.reshape(-1, d), self.world, self.w_bev, self.b_bev, self.w_cam, E_inv, BL, n, P)
+                nq = n
+            else:
+                q_hat = x_ln if x_ln is not None else ops.layernorm_rows(x)
+                nq = 1
+            q1 = ops.linear_tokens(q_hat.reshape(-1, d), self.a1.q)[0].view(BL, nq, H, W, d)
         qm = ops.token_map(nq, H, W, *self.q_win, False)
         km = ops.token_map(n, hp, wp, fh, fw, False, Hv=h, Wv=w)
         a = ops.window_attention(q1, k1, v1, qm, km, self.a1.heads, self.a1.scale, True,

@@ -569,3 +569,23 @@ def scale_channels_(x, gate):
         _lib.check(_lib.lib().cobevt_scale_channels(_ptr(x), _f32(gate), _ptr(x), N, H * W, C, dtype_code(x.dtype), _stream()),
                    "cobevt_scale_channels")
     return x
+
+
+def bev_q_analytic(x, pc_wx, tab, consts, world, E_inv, BL, n, P, eps=1e-5):
+    """Stage-0 query projection without the LayerNorm round trip: x (rows, C) 16-bit with rows == P (shared prior) or
+    BL*P; pc_wx = PackedConv(W', no bias); tab (C,16) fp32 channel table, consts = (qa, qb, qd, ma, mb) (see
+    include/cobevt_b200.h).  Returns q (BL, n, P, C) 16-bit."""
+    C = x.shape[-1]
+    rows = x.numel() // C
+    qx = linear_tokens(x.reshape(rows, C), pc_wx, want16=False, out32=True)[1]
+    stats = torch.empty(rows, 12, dtype=torch.float32, device=x.device)
+    with _timed("eltwise", 0, "row_stats9"):
+        _lib.check(_lib.lib().cobevt_row_stats9(_ptr(x), _f32(tab), _ptr(stats), rows, C, dtype_code(x.dtype), _stream()),
+                   "cobevt_row_stats9")
+    out = torch.empty(BL, n, P, C, dtype=x.dtype, device=x.device)
+    qa, qb, qd, ma, mb = consts
+    with _timed("eltwise", 0, "bev_q_analytic"):
+        _lib.check(_lib.lib().cobevt_bev_q_analytic(_f32(qx), rows, _f32(stats), _f32(world), _f32(tab), _f32(E_inv), _ptr(out),
+                                                    BL, n, P, C, qa, qb, qd, ma, mb, eps, dtype_code(x.dtype), _stream()),
+                   "cobevt_bev_q_analytic")
+    return out

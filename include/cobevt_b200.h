@@ -247,6 +247,17 @@ int cobevt_se_gate(const float* sums, float inv_hw, const float* w1, const float
 /* y[n,p,c] = x[n,p,c] * gate[n,c] (in place allowed) */
 int cobevt_scale_channels(const void* x, const float* gate, void* y, int32_t N, int64_t HW, int32_t C, int32_t dtype,
                           void* stream);
+/* ---- analytic stage-0 query projection: q = W' LN0(x + normalise(bev_embed(world) - c_embed)) + b' without a per-token
+ * reduction or GEMM (fax_modules.py:370-375,387-390 + to_q :189-190; derivation in csrc/eltwise2.cu).
+ * chan_tab (C,20) fp32 = [a, b_, b_bev, w_cam(4), 0 | W'a, W'b_, W'1, b' | W'b_bev, W'w_cam(4), 0, 0, 0] (a, b_ = columns of
+ * bev_embed.weight); n <= min(8, C/8) views;
+ * stats (rows,12) fp32 = channel means of [x, x^2, x a, x b_, x b_bev, x w_cam(4)] from cobevt_row_stats9;
+ * qx (x_rows,C) fp32 = W'x from cobevt_conv2d_nhwc_fwd (y32); x_rows = P (one prior shared by every row) or BL*P;
+ * qa = a.a, qb = b_.b_, qd = 2 a.b_, ma = mean(a), mb = mean(b_); out (BL,n,P,C) 16-bit. */
+int cobevt_row_stats9(const void* x, const float* chan_tab, float* stats, int64_t rows, int32_t C, int32_t dtype, void* stream);
+int cobevt_bev_q_analytic(const float* qx, int64_t x_rows, const float* stats, const float* world, const float* chan_tab,
+                          const float* E_inv, void* out, int32_t BL, int32_t n, int32_t P, int32_t C, float qa, float qb,
+                          float qd, float ma, float mb, float eps, int32_t dtype, void* stream);
 /* NCHW <-> NHWC(Cpad) with dtype conversion; module API boundaries only */
 int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t Cpad,
                    int32_t to_nhwc, int32_t src_dtype, int32_t dst_dtype, void* stream);

@@ -376,3 +376,34 @@ def test_bn_relu2(C):
     assert relerr(yb, F.relu(x.float() * sb + bb)) < 1e-3
     only, none = ops.bn_relu2(x, sa, ba)
     assert none is None and torch.equal(only, ya)
+
+
+# --------------------------------------------------------------------------- analytic stage-0 query projection
+@pytest.mark.parametrize("C,shared,n", [(128, True, 6), (128, False, 5), (32, True, 4), (64, False, 8)])
+def test_bev_q_analytic_vs_direct(C, shared, n):
+    """q = W' LN0(x + normalise(bev_embed(world) - c_embed)) + b' (fax_modules.py:370-375,387-390, to_q :189-190):
+    the closed-form kernel (no per-token reduction, no GEMM over the view-replicated tokens) against the direct formula."""
+    from cobevt_b200 import ops
+    g = torch.Generator().manual_seed(C + shared)
+    BL, H, W = 3, 12, 16
+    P = H * W
+    wq = torch.randn(C, C, generator=g) / math.sqrt(C)
+    bq = torch.randn(C, generator=g) * 0.3
+    wb, bb, wc = torch.randn(C, 2, generator=g), torch.randn(C, generator=g), torch.randn(C, 4, generator=g)
+    x = torch.randn(1 if shared else BL, P, C, generator=g).half()
+    world = (torch.rand(2, P, generator=g) - 0.5) * 100
+    E = torch.randn(BL * n, 4, 4, generator=g)
+    E[:, 3, :] = torch.tensor([0., 0., 0., 1.])
+    a_, b_ = wb[:, 0], wb[:, 1]
+    z = torch.zeros_like(a_)
+    tab = torch.stack([a_, b_, bb] + [wc[:, k] for k in range(4)] + [z] + [wq @ a_, wq @ b_, wq.sum(1), bq] + [wq @ bb] +
+                      [wq @ wc[:, k] for k in range(4)] + [z, z, z], dim=1).contiguous().cuda()
+    consts = (float(a_ @ a_), float(b_ @ b_), float(2 * (a_ @ b_)), float(a_.mean()), float(b_.mean()))
+    pc = ops.PackedConv(wq, None, "cuda")
+    got = ops.bev_q_analytic(x.cuda().reshape(-1, C), pc, tab, consts, world.cuda().contiguous(), E.cuda().contiguous(), BL, n, P)
+    t = E[:, :, 3].reshape(BL, n, 4)
+    e = (wb @ world).T[None, None] + (bb - t @ wc.T)[:, :, None, :]                       # BL n P C
+    y = x.float()[:, None] + e / (e.norm(dim=-1, keepdim=True) + 1e-7)
+    ref = F.layer_norm(y, (C,)) @ wq.half().float().T + bq
+    assert got.shape == ref.shape
+    assert relerr(got, ref) < 2e-3, relerr(got, ref)
