@@ -118,6 +118,7 @@ _ELTWISE_SIGS = {
                             c_i32, c_i32, c_vp],
     "cobevt_se_gate": [c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp],
     "cobevt_scale_channels": [c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp],
+    "cobevt_se_scale": [c_vp, c_vp, c_f32, c_vp, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_i32, c_vp],
     "cobevt_row_stats9": [c_vp, c_vp, c_vp, c_i64, c_i32, c_i32, c_vp],
     "cobevt_bev_q_analytic": [c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_f32, c_f32, c_f32,
                               c_f32, c_f32, c_f32, c_i32, c_vp],

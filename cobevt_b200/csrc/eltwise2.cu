@@ -199,6 +199,45 @@ __global__ void scale_channels_kernel(const uint16_t* __restrict__ x, const floa
   *reinterpret_cast<uint4*>(y + idx * 8) = pk8(f, bf16);
 }
 
+// squeeze-excite gate + its application in one launch: every block recomputes the (tiny) gate of its image into shared
+// memory -- C * Cse * 2 MACs against a launch saved per MBConv block -- then scales its slice of the map in place.
+// grid (blocks per image, N); sums (N, C) as produced by dwconv_kernel.
+__global__ void __launch_bounds__(256) se_scale_kernel(uint16_t* __restrict__ x, const float* __restrict__ sums, float inv_hw,
+                                                       const float* __restrict__ w1, const float* __restrict__ b1,
+                                                       const float* __restrict__ w2, const float* __restrict__ b2, int64_t HW, int C,
+                                                       int Cse, int bf16) {
+  extern __shared__ float sh[];          // gate[C] | mean[C] | hidden[Cse]
+  float* gate = sh;
+  float* mean = sh + C;
+  float* hid = sh + 2 * C;
+  const int n = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mean[c] = sums[(int64_t)n * C + c] * inv_hw;
+  __syncthreads();
+  for (int j = threadIdx.x; j < Cse; j += blockDim.x) {
+    float a = b1[j];
+    for (int c = 0; c < C; ++c) a = fmaf(w1[j * C + c], mean[c], a);
+    hid[j] = swish(a);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = b2[c];
+    for (int j = 0; j < Cse; ++j) a = fmaf(w2[c * Cse + j], hid[j], a);
+    gate[c] = 1.0f / (1.0f + __expf(-a));
+  }
+  __syncthreads();
+  const int cg = C / 8;
+  const int64_t nvec = HW * cg;
+  uint16_t* xi = x + (int64_t)n * HW * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cg);
+    float f[8];
+    up8(*reinterpret_cast<const uint4*>(xi + i * 8), bf16, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= gate[c8 * 8 + j];
+    *reinterpret_cast<uint4*>(xi + i * 8) = pk8(f, bf16);
+  }
+}
+
 // ------------------------------------------------------------------ analytic BEV query projection (stage 0 of SinBEVT)
 // q[b,n,p,:] = W' LN0(x[b,p,:] + e / (|e| + 1e-7)) + b',  e = a wx_p + b_ wy_p + c_{b,n}  (fax_modules.py:370-375,387-390
 // and to_q :189-190, W' / b' = the projection with the LayerNorm affine folded in).  e is AFFINE in the cell's world
@@ -436,4 +475,16 @@ extern "C" int cobevt_bev_q_analytic(const float* qx, int64_t x_rows, const floa
   else if (C == 64) bev_q_kernel<64><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
   else bev_q_kernel<32><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
   return cobevt::check_launch("bev_q_analytic");
+}
+
+extern "C" int cobevt_se_scale(void* x, const float* sums, float inv_hw, const float* w1, const float* b1, const float* w2,
+                               const float* b2, int32_t N, int64_t HW, int32_t C, int32_t Cse, int32_t dtype, void* stream) {
+  if (!x || !sums || !w1 || !b1 || !w2 || !b2 || N <= 0 || N > 65535 || C % 8 || Cse <= 0 || (2 * C + Cse) * 4 > 48 * 1024)
+    return fail(COBEVT_ERR_SHAPE, "se_scale: bad args");
+  int64_t bpi = (HW * (C / 8) + 256 * 4 - 1) / (256 * 4);          // ~4 vectors per thread
+  if (bpi < 1) bpi = 1;
+  if (bpi > 1024) bpi = 1024;
+  dim3 grid((unsigned)bpi, (unsigned)N);
+  se_scale_kernel<<<grid, 256, (size_t)(2 * C + Cse) * sizeof(float), ST(stream)>>>((uint16_t*)x, sums, inv_hw, w1, b1, w2, b2, HW, C, Cse, dtype);
+  return cobevt::check_launch("se_scale");
 }

@@ -545,7 +545,7 @@ class MBConvPlan:
         self.b2 = _dev_f32(blk._se_expand.bias, device)
         self.project = PackedConv(*fold_conv_bn(blk._project_conv, blk._bn2), device, dtype)
 
-    def run(self, x):
+    def run(self, x, sums_pool):
         N, H, W, _ = x.shape
         y = x
         if self.expand is not None:
@@ -553,10 +553,9 @@ class MBConvPlan:
         C = y.shape[-1]
         pb, pa = self.pad
         OH, OW = (H + pb + pa - self.k) // self.stride + 1, (W + pb + pa - self.k) // self.stride + 1
-        sums = torch.zeros(N, C, dtype=torch.float32, device=x.device)
+        sums = sums_pool[:N * C].view(N, C)              # zeroed once per forward for all blocks (EffNetPlan.run)
         y = ops.dwconv_swish(y, self.wd, self.bd, self.k, self.stride, pb, pb, OH, OW, sums=sums)
-        gate = ops.se_gate(sums, OH * OW, self.w1, self.b1, self.w2, self.b2)
-        ops.scale_channels_(y, gate)
+        ops.se_scale_(y, sums, self.w1, self.b1, self.w2, self.b2)
         return ops.conv2d_nhwc(y, self.project, res=x if self.skip else None)[0]
 
 
@@ -595,8 +594,14 @@ class EffNetPlan:
         x = ops.pack_rgb4_padded(images_nchw, self.dtype, pb, pb, Hp, Wp, nchw=True, mean=mean, std=std).view(N, Hp, Wp // 2, 8)
         x = ops.conv2d_nhwc(x, self.stem, stride=(2, 1), pad=0, act=ACT_SWISH, out_hw=(OH, OW))[0]
         feats = []
+        # one zeroed pool serves the squeeze sums of every block (each block takes its own slice: no re-zeroing)
+        need = sum(N * b.wd.shape[-1] for blocks in self.groups for b in blocks)
+        pool = torch.zeros(need, dtype=torch.float32, device=x.device)
+        off = 0
         for blocks in self.groups:
             for blk in blocks:
-                x = blk.run(x)
+                c = N * blk.wd.shape[-1]
+                x = blk.run(x, pool[off:off + c])
+                off += c
             feats.append(x)
         return feats

@@ -589,3 +589,12 @@ def bev_q_analytic(x, pc_wx, tab, consts, world, E_inv, BL, n, P, eps=1e-5):
                                                     BL, n, P, C, qa, qb, qd, ma, mb, eps, dtype_code(x.dtype), _stream()),
                    "cobevt_bev_q_analytic")
     return out
+
+
+def se_scale_(x, sums, w1, b1, w2, b2):
+    """squeeze-excite in one launch: x (N,H,W,C) 16-bit *= sigmoid(W2 swish(W1 mean + b1) + b2), mean = sums / (H W)."""
+    N, H, W, C = x.shape
+    with _timed("eltwise", 0, "se_scale"):
+        _lib.check(_lib.lib().cobevt_se_scale(_ptr(x), _f32(sums), 1.0 / (H * W), _f32(w1), _f32(b1), _f32(w2), _f32(b2), N, H * W, C,
+                                              w1.shape[0], dtype_code(x.dtype), _stream()), "cobevt_se_scale")
+    return x

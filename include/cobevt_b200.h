@@ -244,6 +244,9 @@ int cobevt_dwconv_swish(const void* x, const float* w, const float* bias, void* 
 /* gate (N,C) = sigmoid(W2 swish(W1 (sums * inv_hw) + b1) + b2); w1 (Cse,C), w2 (C,Cse) fp32 */
 int cobevt_se_gate(const float* sums, float inv_hw, const float* w1, const float* b1, const float* w2,
                    const float* b2, float* gate, int32_t N, int32_t C, int32_t Cse, void* stream);
+/* x[n,p,c] *= gate[n,c] with the gate of cobevt_se_gate recomputed per block (one launch instead of two) */
+int cobevt_se_scale(void* x, const float* sums, float inv_hw, const float* w1, const float* b1, const float* w2,
+                    const float* b2, int32_t N, int64_t HW, int32_t C, int32_t Cse, int32_t dtype, void* stream);
 /* y[n,p,c] = x[n,p,c] * gate[n,c] (in place allowed) */
 int cobevt_scale_channels(const void* x, const float* gate, void* y, int32_t N, int64_t HW, int32_t C, int32_t dtype,
                           void* stream);
