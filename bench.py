@@ -317,7 +317,7 @@ def extra_configs(dev):
             mn.load_state_dict(synth.synth_state_dict(mn, seed=0))
             mn = mn.to(dev)
             sweep = {}
-            for S in (1, 2, 8):
+            for S in (1, 2, 4, 8, 16):
                 batch = synth.to_device(synth.synth_batch(dict(cfgn, max_cav=5), record_len=(5,) * S, n_cams=CAMS, seed=1), dev)
                 sh = ShardedCorpBEVT(mn, 0, 1, graphs=True)
                 ms = _time_fn(lambda: sh(batch, [5] * S, batch["transformation_matrix"]), iters=10)
