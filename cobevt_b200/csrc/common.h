@@ -4,6 +4,8 @@
 #include <cuda.h>          // CUtensorMap (the encoder is fetched through the runtime, libcuda is not linked)
 #include <cstdio>
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 #include "../../include/cobevt_b200.h"
 
 namespace cobevt {
@@ -42,6 +44,34 @@ inline int num_sms() {
     sms[dev] = v > 0 ? v : 148;
   }
   return sms[dev];
+}
+
+// Programmatic dependent launch: every kernel of the library is launched with the stream-serialisation attribute, so in a
+// stream (or a captured graph) kernel N+1's CTAs may be scheduled, run their prologue (barrier init, TMEM allocation,
+// constant weight / bias staging) and park in `griddepcontrol.wait` while kernel N drains.  Each kernel executes
+// pdl_wait() (sm100.cuh) before its first access to memory another kernel may have written or may still read.
+// COBEVT_PDL=0 in the environment launches everything fully serialised (A/B timing, debugging).
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("COBEVT_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // Timing-experiment knobs (COBEVT_CONV_DEBUG / COBEVT_ATTN_DEBUG produce WRONG results by design) exist only in

@@ -187,9 +187,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   __shared__ float2 sXch[2][2][2][128];           // [team][tile parity][column half][row] = (mean, M2)
 
   const CobevtConvParams& p = a.p;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = warp_index_uniform();                  // see sm100.cuh: keeps role / counter state in uniform registers
   const int KB = a.KB;
 
+  // Programmatic dependent launch: the next kernel may be scheduled as soon as every CTA of this grid is resident;
+  // this CTA's prologue (barriers, TMEM, constant bias / LN vectors, resident weights) runs before pdl_wait(), i.e.
+  // possibly while the previous kernel of the stream is still draining.  Activations are touched only after it.
+  pdl_trigger();
   if (tid == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) {
       mbar_init(&a_full[s], a.use_tma ? 1 : 128);
@@ -232,6 +237,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   if (warp < 4 && !a.use_tma) {
     // ================================ A producers ========================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKERS));
+    pdl_wait();
     const uint8_t* xbytes = reinterpret_cast<const uint8_t*>(p.x);
     uint32_t it = 0;   // stage uses issued so far (across tiles)
     int ps = 0;        // stage of use `it`            (incremental: no runtime divisions in the loops)
@@ -353,6 +359,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   } else if (team >= 0) {
     // ================================ epilogue (8 warps per team) ==========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_WORKERS));
+    pdl_wait();                       // residual reads and output stores follow the previous kernel
     const int q4 = e & 3;             // TMEM lane quarter (== warp % 4)
     const int hf = e >> 2;            // column half
     const bool active = (BN >= 64) || (hf == 0);
@@ -572,6 +579,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
         mbar_arrive_expect_tx(&b_res_full, (uint32_t)(KB * kBStage));
         for (int kb = 0; kb < KB; ++kb) bulk_g2s(sB + kb * kBStage, wbase + (int64_t)kb * kBStage, kBStage, &b_res_full);
       }
+      pdl_wait();                         // weights are constants; the A operand is the previous kernel's output
       int bs = 0, ps = 0;                 // B / A ring positions and the parities to wait for
       uint32_t bph = 1, pph = 1;
       auto load_b = [&](const uint8_t* wb, int kb) {
@@ -944,7 +952,7 @@ int launch(KArgs& a, cudaStream_t st) {
   }
   const int num_sms = cobevt::num_sms();
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
-  conv_gemm_kernel<BN><<<grid, NUM_THREADS, (size_t)smem, st>>>(a);
+  cobevt::launch_k(conv_gemm_kernel<BN>, grid, NUM_THREADS, (size_t)smem, st, a);
   return cobevt::check_launch("conv_gemm_kernel");
 }
 

@@ -94,6 +94,8 @@ __device__ __forceinline__ void ln_row(float* v, int per, int C, int lane, float
 
 // ------------------------------------------------------------------ pack_rgb8
 __global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int64_t npix, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   const float r = x[i * 3], g = x[i * 3 + 1], b = x[i * 3 + 2];
@@ -107,6 +109,8 @@ __global__ void pack_rgb8_kernel(const float* __restrict__ x, uint16_t* __restri
 // left): the 7x7/s2 stem then needs no bounds checks and its taps start on 16-byte boundaries.
 __global__ void pack_rgb4_pad_kernel(const float* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
                                      int Hp, int Wp, int pt, int pl, int nchw, float3 mean, float3 istd, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   // two output pixels (one 16-byte store) per thread, Wp is even: twice the bytes in flight of the one-pixel version
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int Wh = Wp >> 1;
@@ -154,6 +158,8 @@ __device__ __forceinline__ uint32_t max2_16(uint32_t a, uint32_t b) {
 template <bool BF16>
 __global__ void __launch_bounds__(256) maxpool_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H,
                                                       int W, int C, int OH, int OW) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int cg = C / 8;
   const int OWp = (OW + 1) >> 1;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -202,6 +208,8 @@ template <bool SAME_CG>
 __global__ void __launch_bounds__(256) bn_relu2_kernel(const uint16_t* __restrict__ x, const float* __restrict__ sa,
                                 const float* __restrict__ ba, uint16_t* __restrict__ ya, const float* __restrict__ sb,
                                 const float* __restrict__ bb, uint16_t* __restrict__ yb, int64_t nvec, int C, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   constexpr int VPT = 4;
   const int cg = C / 8;
   const int64_t base = (int64_t)blockIdx.x * (256 * VPT) + threadIdx.x;
@@ -258,6 +266,8 @@ __global__ void __launch_bounds__(256) ray_embed_kernel(const float* __restrict_
                                  const float* __restrict__ w_img, const float* __restrict__ w_cam,
                                  uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
                                  int C, int invert_I, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v = blockIdx.y;
   float Ii[9];
@@ -336,6 +346,8 @@ __global__ void __launch_bounds__(256) bev_query_kernel(const uint16_t* __restri
                                  const float* __restrict__ w_bev, const float* __restrict__ b_bev,
                                  const float* __restrict__ w_cam, const float* __restrict__ E_inv,
                                  uint16_t* __restrict__ out, int BL, int n, int P, int C, float eps, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int v = blockIdx.y;
   const int b = v / n;
@@ -442,6 +454,8 @@ __global__ void __launch_bounds__(256) ray_embed_grouped_kernel(const float* __r
                                  const float* __restrict__ w_img, const float* __restrict__ w_cam,
                                  uint16_t* __restrict__ out, int NV, int h, int w, float image_h, float image_w,
                                  int invert_I, int bf16, int cpb) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   constexpr int C = CPL * LPC, CPW = 32 / LPC;          // channels, cells per warp and step
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane % LPC, sub = lane / LPC;         // channel group, cell slot inside the warp
@@ -508,6 +522,8 @@ __global__ void __launch_bounds__(256) bev_query_grouped_kernel(const uint16_t* 
                                  const float* __restrict__ w_bev, const float* __restrict__ b_bev,
                                  const float* __restrict__ w_cam, const float* __restrict__ E_inv,
                                  uint16_t* __restrict__ out, int n, int P, float eps, int bf16, int cpb) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   constexpr int C = CPL * LPC, CPW = 32 / LPC;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int grp = lane % LPC, sub = lane / LPC;
@@ -590,6 +606,8 @@ __global__ void __launch_bounds__(256) bev_query_grouped_kernel(const uint16_t* 
 __global__ void layernorm_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, uint16_t* __restrict__ y, int64_t rows, int C,
                                  float eps, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
@@ -603,6 +621,8 @@ __global__ void layernorm_kernel(const uint16_t* __restrict__ x, const float* __
 // x (B, L, P, C) -> y (B, P, C) = LN0(mean_l x)   (swap_fusion_modules.py:275-278)
 __global__ void mean_views_ln_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int B, int L, int P,
                                      int C, float eps, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (row >= (int64_t)B * P) return;
@@ -631,6 +651,8 @@ __global__ void sttf_kernel(const uint16_t* __restrict__ x, const float* __restr
                             const int64_t* __restrict__ record_len, uint16_t* __restrict__ out,
                             uint8_t* __restrict__ mask, int B, int L, int H, int W, int C, float inv_disc,
                             int use_roi, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int lane = threadIdx.x & 31;
   const int64_t cell = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (cell >= (int64_t)B * L * H * W) return;
@@ -694,6 +716,8 @@ __global__ void sttf_kernel(const uint16_t* __restrict__ x, const float* __restr
 // nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True), nuscenes decoder.py:13
 __global__ void upsample_bilinear2x_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W,
                                            int C, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int cg = C / 8, OH = 2 * H, OW = 2 * W;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * OH * OW * cg) return;
@@ -735,6 +759,8 @@ __global__ void upsample_bilinear2x_kernel(const uint16_t* __restrict__ x, uint1
 // DecoderBlock.forward, nuscenes decoder.py:28-36 (F.interpolate default = nearest)
 __global__ void add_nearest_relu_kernel(uint16_t* __restrict__ y, const uint16_t* __restrict__ up, int N, int H, int W,
                                         int h, int w, int C, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int cg = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * H * W * cg) return;
@@ -762,6 +788,8 @@ __global__ void add_nearest_relu_kernel(uint16_t* __restrict__ y, const uint16_t
 // batch['intrinsics'].inverse(), batch['extrinsics'].inverse()  (encoder_pyramid_axial.py:538-539)
 template <int D>
 __global__ void invert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a[D][2 * D];
@@ -811,6 +839,8 @@ __device__ __forceinline__ void st_any(void* p, int64_t i, int dt, float v) {
 // src NCHW (C channels) -> dst NHWC with Cpad channels (zero filled), or the reverse
 __global__ void permute_kernel(const void* __restrict__ src, void* __restrict__ dst, int N, int C, int H, int W,
                                int Cpad, int to_nhwc, int sdt, int ddt) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (to_nhwc) {
     const int64_t total = (int64_t)N * H * W * Cpad;
@@ -842,7 +872,7 @@ using cobevt::fail;
 
 extern "C" int cobevt_pack_rgb8(const float* x, void* y, int64_t npix, int32_t dtype, void* stream) {
   if (!x || !y || npix <= 0) return fail(COBEVT_ERR_SHAPE, "pack_rgb8: bad args");
-  pack_rgb8_kernel<<<blocks_for(npix, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, npix, dtype);
+  cobevt::launch_k(pack_rgb8_kernel, blocks_for(npix, 256), 256, 0, ST(stream), x, (uint16_t*)y, npix, dtype);
   return cobevt::check_launch("pack_rgb8");
 }
 
@@ -854,7 +884,7 @@ extern "C" int cobevt_pack_rgb4_padded(const float* x, void* y, int32_t N, int32
   // mean3 / std3 are HOST pointers (3 floats each) or NULL: the Normalize of encoder_pyramid_axial.py:41-49
   float3 mean = make_float3(0.f, 0.f, 0.f), istd = make_float3(1.f, 1.f, 1.f);
   if (mean3 && std3) { mean = make_float3(mean3[0], mean3[1], mean3[2]); istd = make_float3(1.f / std3[0], 1.f / std3[1], 1.f / std3[2]); }
-  pack_rgb4_pad_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, src_nchw, mean, istd, dtype);
+  cobevt::launch_k(pack_rgb4_pad_kernel, blocks_for(total, 256), 256, 0, ST(stream), x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, src_nchw, mean, istd, dtype);
   return cobevt::check_launch("pack_rgb4_padded");
 }
 
@@ -863,8 +893,8 @@ extern "C" int cobevt_maxpool3x3s2_nhwc(const void* x, void* y, int32_t N, int32
   if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "maxpool: bad args");
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)N * OH * ((OW + 1) / 2) * (C / 8);
-  if (dtype == COBEVT_BF16) maxpool_kernel<true><<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
-  else maxpool_kernel<false><<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
+  if (dtype == COBEVT_BF16) cobevt::launch_k(maxpool_kernel<true>, blocks_for(total, 256), 256, 0, ST(stream), (const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
+  else cobevt::launch_k(maxpool_kernel<false>, blocks_for(total, 256), 256, 0, ST(stream), (const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW);
   return cobevt::check_launch("maxpool");
 }
 
@@ -873,10 +903,10 @@ extern "C" int cobevt_bn_relu2(const void* x, const float* sa, const float* ba, 
   if (!x || !sa || !ba || !ya || C % 8 || (yb && (!sb || !bb))) return fail(COBEVT_ERR_SHAPE, "bn_relu2: bad args");
   const int64_t nvec = rows * (C / 8);
   if (256 % (C / 8) == 0)
-    bn_relu2_kernel<true><<<blocks_for(nvec, 1024), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
+    cobevt::launch_k(bn_relu2_kernel<true>, blocks_for(nvec, 1024), 256, 0, ST(stream), (const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
                                                                          (uint16_t*)yb, nvec, C, dtype);
   else
-    bn_relu2_kernel<false><<<blocks_for(nvec, 1024), 256, 0, ST(stream)>>>((const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
+    cobevt::launch_k(bn_relu2_kernel<false>, blocks_for(nvec, 1024), 256, 0, ST(stream), (const uint16_t*)x, sa, ba, (uint16_t*)ya, sb, bb,
                                                                           (uint16_t*)yb, nvec, C, dtype);
   return cobevt::check_launch("bn_relu2");
 }
@@ -898,14 +928,14 @@ extern "C" int cobevt_ray_embed(const float* I_inv, const float* E_inv, const fl
   const int cpb = cells_per_block((int64_t)h * w, NV);
   dim3 gridg((h * w + cpb - 1) / cpb, NV);
   dim3 grid((h * w + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, NV);
-  if (C == 128) ray_embed_grouped_kernel<16, 8><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
-  else if (C == 64) ray_embed_grouped_kernel<8, 8><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
-  else if (C == 32) ray_embed_grouped_kernel<8, 4><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
-  else if (C == 256) ray_embed_grouped_kernel<16, 16><<<gridg, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
-  else if (C == 128) ray_embed_kernel<4><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
-  else if (C == 32) ray_embed_kernel<1><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
-  else if (C == 64) ray_embed_kernel<2><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
-  else ray_embed_kernel<8><<<grid, 256, 0, ST(stream)>>>(I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  if (C == 128) cobevt::launch_k(ray_embed_grouped_kernel<16, 8>, gridg, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 64) cobevt::launch_k(ray_embed_grouped_kernel<8, 8>, gridg, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 32) cobevt::launch_k(ray_embed_grouped_kernel<8, 4>, gridg, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 256) cobevt::launch_k(ray_embed_grouped_kernel<16, 16>, gridg, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, invert_intrinsic, dtype, cpb);
+  else if (C == 128) cobevt::launch_k(ray_embed_kernel<4>, grid, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else if (C == 32) cobevt::launch_k(ray_embed_kernel<1>, grid, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else if (C == 64) cobevt::launch_k(ray_embed_kernel<2>, grid, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
+  else cobevt::launch_k(ray_embed_kernel<8>, grid, 256, 0, ST(stream), I_inv, E_inv, w_img, w_cam, (uint16_t*)out, NV, h, w, image_h, image_w, C, invert_intrinsic, dtype);
   return cobevt::check_launch("ray_embed");
 }
 
@@ -917,28 +947,28 @@ extern "C" int cobevt_bev_query(const void* x, int64_t x_rows, const float* worl
   const int cpb = cells_per_block(P, BL * n);
   dim3 gridg((P + cpb - 1) / cpb, BL * n);
   dim3 grid((P + CELLS_PER_BLOCK - 1) / CELLS_PER_BLOCK, BL * n);
-  if (C == 128) bev_query_grouped_kernel<16, 8><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
-  else if (C == 64) bev_query_grouped_kernel<8, 8><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
-  else if (C == 32) bev_query_grouped_kernel<8, 4><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
-  else if (C == 256) bev_query_grouped_kernel<16, 16><<<gridg, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
-  else if (C == 128) bev_query_kernel<4><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
-  else if (C == 32) bev_query_kernel<1><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
-  else if (C == 64) bev_query_kernel<2><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
-  else bev_query_kernel<8><<<grid, 256, 0, ST(stream)>>>((const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  if (C == 128) cobevt::launch_k(bev_query_grouped_kernel<16, 8>, gridg, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 64) cobevt::launch_k(bev_query_grouped_kernel<8, 8>, gridg, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 32) cobevt::launch_k(bev_query_grouped_kernel<8, 4>, gridg, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 256) cobevt::launch_k(bev_query_grouped_kernel<16, 16>, gridg, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, n, P, eps, dtype, cpb);
+  else if (C == 128) cobevt::launch_k(bev_query_kernel<4>, grid, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else if (C == 32) cobevt::launch_k(bev_query_kernel<1>, grid, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else if (C == 64) cobevt::launch_k(bev_query_kernel<2>, grid, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
+  else cobevt::launch_k(bev_query_kernel<8>, grid, 256, 0, ST(stream), (const uint16_t*)x, x_rows, world, w_bev, b_bev, w_cam, E_inv, (uint16_t*)out, BL, n, P, C, eps, dtype);
   return cobevt::check_launch("bev_query");
 }
 
 extern "C" int cobevt_layernorm_rows(const void* x, const float* gamma, const float* beta, void* y, int64_t rows,
                                       int32_t C, float eps, int32_t dtype, void* stream) {
   if (!x || !y || !ok_c(C) || ((gamma == nullptr) != (beta == nullptr))) return fail(COBEVT_ERR_SHAPE, "layernorm: bad args");
-  layernorm_kernel<<<blocks_for(rows * 32, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, gamma, beta, (uint16_t*)y, rows, C, eps, dtype);
+  cobevt::launch_k(layernorm_kernel, blocks_for(rows * 32, 256), 256, 0, ST(stream), (const uint16_t*)x, gamma, beta, (uint16_t*)y, rows, C, eps, dtype);
   return cobevt::check_launch("layernorm");
 }
 
 extern "C" int cobevt_mean_views_ln(const void* x, void* y, int32_t B, int32_t L, int32_t P, int32_t C, float eps,
                                      int32_t dtype, void* stream) {
   if (!x || !y || !ok_c(C) || L <= 0) return fail(COBEVT_ERR_SHAPE, "mean_views_ln: bad args");
-  mean_views_ln_kernel<<<blocks_for((int64_t)B * P * 32, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, B, L, P, C, eps, dtype);
+  cobevt::launch_k(mean_views_ln_kernel, blocks_for((int64_t)B * P * 32, 256), 256, 0, ST(stream), (const uint16_t*)x, (uint16_t*)y, B, L, P, C, eps, dtype);
   return cobevt::check_launch("mean_views_ln");
 }
 
@@ -948,7 +978,7 @@ extern "C" int cobevt_sttf_regroup(const void* x, const float* tm, const int64_t
   if (!x || !tm || !record_len || !out || !mask || !ok_c(C)) return fail(COBEVT_ERR_SHAPE, "sttf: bad args");
   const float inv_disc = 1.0f / (discrete_ratio * downsample_rate);
   const int64_t threads = (int64_t)B * L * H * W * 32;
-  sttf_kernel<<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, tm, record_len, (uint16_t*)out, mask, B, L, H,
+  cobevt::launch_k(sttf_kernel, blocks_for(threads, 256), 256, 0, ST(stream), (const uint16_t*)x, tm, record_len, (uint16_t*)out, mask, B, L, H,
                                                                 W, C, inv_disc, use_roi_mask, dtype);
   return cobevt::check_launch("sttf");
 }
@@ -957,7 +987,7 @@ extern "C" int cobevt_upsample_bilinear2x(const void* x, void* y, int32_t N, int
                                            void* stream) {
   if (!x || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "upsample_bilinear2x: bad args");
   const int64_t total = (int64_t)N * 4 * H * W * (C / 8);
-  upsample_bilinear2x_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, (uint16_t*)y, N, H, W, C, dtype);
+  cobevt::launch_k(upsample_bilinear2x_kernel, blocks_for(total, 256), 256, 0, ST(stream), (const uint16_t*)x, (uint16_t*)y, N, H, W, C, dtype);
   return cobevt::check_launch("upsample_bilinear2x");
 }
 
@@ -965,14 +995,14 @@ extern "C" int cobevt_add_nearest_relu(void* y, const void* up, int32_t N, int32
                                         int32_t C, int32_t dtype, void* stream) {
   if (!y || !up || C % 8) return fail(COBEVT_ERR_SHAPE, "add_nearest_relu: bad args");
   const int64_t total = (int64_t)N * H * W * (C / 8);
-  add_nearest_relu_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>((uint16_t*)y, (const uint16_t*)up, N, H, W, h, w, C, dtype);
+  cobevt::launch_k(add_nearest_relu_kernel, blocks_for(total, 256), 256, 0, ST(stream), (uint16_t*)y, (const uint16_t*)up, N, H, W, h, w, C, dtype);
   return cobevt::check_launch("add_nearest_relu");
 }
 
 extern "C" int cobevt_invert_matrices(const float* src, float* dst, int32_t n, int32_t dim, void* stream) {
   if (!src || !dst || n <= 0 || (dim != 3 && dim != 4)) return fail(COBEVT_ERR_SHAPE, "invert_matrices: dim must be 3 or 4");
-  if (dim == 3) invert_kernel<3><<<blocks_for(n, 128), 128, 0, ST(stream)>>>(src, dst, n);
-  else invert_kernel<4><<<blocks_for(n, 128), 128, 0, ST(stream)>>>(src, dst, n);
+  if (dim == 3) cobevt::launch_k(invert_kernel<3>, blocks_for(n, 128), 128, 0, ST(stream), src, dst, n);
+  else cobevt::launch_k(invert_kernel<4>, blocks_for(n, 128), 128, 0, ST(stream), src, dst, n);
   return cobevt::check_launch("invert_matrices");
 }
 
@@ -980,6 +1010,6 @@ extern "C" int cobevt_permute(const void* src, void* dst, int32_t N, int32_t C, 
                                int32_t to_nhwc, int32_t src_dtype, int32_t dst_dtype, void* stream) {
   if (!src || !dst || Cpad < C) return fail(COBEVT_ERR_SHAPE, "permute: bad args");
   const int64_t total = to_nhwc ? (int64_t)N * H * W * Cpad : (int64_t)N * C * H * W;
-  permute_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(src, dst, N, C, H, W, Cpad, to_nhwc, src_dtype, dst_dtype);
+  cobevt::launch_k(permute_kernel, blocks_for(total, 256), 256, 0, ST(stream), src, dst, N, C, H, W, Cpad, to_nhwc, src_dtype, dst_dtype);
   return cobevt::check_launch("permute");
 }

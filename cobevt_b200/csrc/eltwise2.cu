@@ -42,6 +42,8 @@ inline unsigned blocks_for(int64_t threads, int bs) { return (unsigned)((threads
 // one 8-byte store.
 __global__ void stage_rgb_u8_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int Hp,
                                     int Wp, int pt, int pl, int bgr, float3 sc, float3 sh, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * Hp * Wp) return;
   const int xp = (int)(i % Wp);
@@ -62,6 +64,8 @@ __global__ void stage_rgb_u8_kernel(const uint8_t* __restrict__ x, uint16_t* __r
 // ------------------------------------------------------------------ softmax + argmax over the class axis (NCHW fp32)
 __global__ void softmax_argmax_kernel(const float* __restrict__ seg, float* __restrict__ prob, int64_t* __restrict__ amap,
                                       int N, int C, int64_t HW) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)N * HW) return;
   const int64_t n = i / HW, p = i - n * HW;
@@ -85,6 +89,8 @@ __global__ void softmax_argmax_kernel(const float* __restrict__ seg, float* __re
 // ------------------------------------------------------------------ nearest resize (F.interpolate default mode)
 __global__ void resize_nearest_kernel(const uint16_t* __restrict__ x, uint16_t* __restrict__ y, int N, int H, int W, int C,
                                       int OH, int OW, float sy, float sx) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int cg = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * OH * OW * cg) return;
@@ -106,6 +112,8 @@ template <int K>
 __global__ void dwconv_kernel(const uint16_t* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
                               uint16_t* __restrict__ y, float* __restrict__ sums, int N, int H, int W, int C, int OH, int OW,
                               int stride, int pt, int pl, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   // grid: (ceil(OH*OW / blockDim.y), C/8 groups folded into threadIdx.x, N)
   const int cg = C / 8;
   const int g = blockIdx.y * blockDim.x + threadIdx.x;          // channel group
@@ -164,6 +172,8 @@ __global__ void dwconv_kernel(const uint16_t* __restrict__ x, const float* __res
 __global__ void se_gate_kernel(const float* __restrict__ sums, float inv_hw, const float* __restrict__ w1,
                                const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                float* __restrict__ gate, int C, int Cse) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   extern __shared__ float sh[];          // mean[C] | hidden[Cse]
   float* mean = sh;
   float* hid = sh + C;
@@ -186,6 +196,8 @@ __global__ void se_gate_kernel(const float* __restrict__ sums, float inv_hw, con
 // y[n, p, c] = x[n, p, c] * gate[n, c]   (in place allowed)
 __global__ void scale_channels_kernel(const uint16_t* __restrict__ x, const float* __restrict__ gate, uint16_t* __restrict__ y,
                                       int N, int64_t HW, int C, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   const int cg = C / 8;
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)N * HW * cg) return;
@@ -206,6 +218,8 @@ __global__ void __launch_bounds__(256) se_scale_kernel(uint16_t* __restrict__ x,
                                                        const float* __restrict__ w1, const float* __restrict__ b1,
                                                        const float* __restrict__ w2, const float* __restrict__ b2, int64_t HW, int C,
                                                        int Cse, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   extern __shared__ float sh[];          // gate[C] | mean[C] | hidden[Cse]
   float* gate = sh;
   float* mean = sh + C;
@@ -253,6 +267,8 @@ __global__ void __launch_bounds__(256) se_scale_kernel(uint16_t* __restrict__ x,
 template <int C>
 __global__ void __launch_bounds__(256) row_stats9_kernel(const uint16_t* __restrict__ x, const float* __restrict__ tab,
                                                          float* __restrict__ stats, int64_t rows, int bf16) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   constexpr int LPT = C / 8;                       // lanes per row (8 channels each)
   const int lane = threadIdx.x & 31, g = lane % LPT;
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPT;
@@ -293,6 +309,8 @@ __global__ void __launch_bounds__(256) bev_q_kernel(const float* __restrict__ qx
                                                     const float* __restrict__ world, const float* __restrict__ tab,
                                                     const float* __restrict__ E_inv, uint16_t* __restrict__ out, int n, int P,
                                                     float qa, float qb, float qd, float ma, float mb, float eps, int bf16, int cpb) {
+  sm100::pdl_trigger();
+  sm100::pdl_wait();
   constexpr int LPT = C / 8, TPB = 256 / LPT;      // lanes per token, tokens per block iteration
   constexpr int MAXV = 8;
   __shared__ __align__(16) float sCc[MAXV][C];     // Cc_{b,v} = Cb - M4 t_v
@@ -399,20 +417,20 @@ extern "C" int cobevt_stage_rgb_u8(const uint8_t* x, void* y, int32_t N, int32_t
     sh = make_float3(-mean3[0] / std3[0], -mean3[1] / std3[1], -mean3[2] / std3[2]);
   }
   const int64_t total = (int64_t)N * Hp * Wp;
-  stage_rgb_u8_kernel<<<blocks_for(total, 256), 256, 0, ST(stream)>>>(x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, bgr, sc, sh, dtype);
+  cobevt::launch_k(stage_rgb_u8_kernel, blocks_for(total, 256), 256, 0, ST(stream), x, (uint16_t*)y, N, H, W, Hp, Wp, pad_top, pad_left, bgr, sc, sh, dtype);
   return cobevt::check_launch("stage_rgb_u8");
 }
 
 extern "C" int cobevt_softmax_argmax(const float* seg, float* prob, int64_t* amap, int32_t N, int32_t C, int64_t HW, void* stream) {
   if (!seg || !prob || !amap || N <= 0 || C <= 0 || HW <= 0) return fail(COBEVT_ERR_SHAPE, "softmax_argmax: bad args");
-  softmax_argmax_kernel<<<blocks_for((int64_t)N * HW, 256), 256, 0, ST(stream)>>>(seg, prob, amap, N, C, HW);
+  cobevt::launch_k(softmax_argmax_kernel, blocks_for((int64_t)N * HW, 256), 256, 0, ST(stream), seg, prob, amap, N, C, HW);
   return cobevt::check_launch("softmax_argmax");
 }
 
 extern "C" int cobevt_resize_nearest(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, int32_t OH, int32_t OW,
                                      float src_per_dst_h, float src_per_dst_w, void* stream) {
   if (!x || !y || C % 8 || OH <= 0 || OW <= 0) return fail(COBEVT_ERR_SHAPE, "resize_nearest: bad args");
-  resize_nearest_kernel<<<blocks_for((int64_t)N * OH * OW * (C / 8), 256), 256, 0, ST(stream)>>>(
+  cobevt::launch_k(resize_nearest_kernel, blocks_for((int64_t)N * OH * OW * (C / 8), 256), 256, 0, ST(stream), 
       (const uint16_t*)x, (uint16_t*)y, N, H, W, C, OH, OW, src_per_dst_h, src_per_dst_w);
   return cobevt::check_launch("resize_nearest");
 }
@@ -428,8 +446,8 @@ extern "C" int cobevt_dwconv_swish(const void* x, const float* w, const float* b
   dim3 block(bx, by), grid((OH * OW + by - 1) / by, (cg + bx - 1) / bx, N);
   const size_t sm = sums ? (size_t)bx * by * 8 * sizeof(float) : 0;
   if (sm > 48 * 1024) return fail(COBEVT_ERR_UNSUPPORTED, "dwconv_swish: reduction scratch too large");
-  if (K == 3) dwconv_kernel<3><<<grid, block, sm, ST(stream)>>>((const uint16_t*)x, w, bias, (uint16_t*)y, sums, N, H, W, C, OH, OW, stride, pad_top, pad_left, dtype);
-  else dwconv_kernel<5><<<grid, block, sm, ST(stream)>>>((const uint16_t*)x, w, bias, (uint16_t*)y, sums, N, H, W, C, OH, OW, stride, pad_top, pad_left, dtype);
+  if (K == 3) cobevt::launch_k(dwconv_kernel<3>, grid, block, sm, ST(stream), (const uint16_t*)x, w, bias, (uint16_t*)y, sums, N, H, W, C, OH, OW, stride, pad_top, pad_left, dtype);
+  else cobevt::launch_k(dwconv_kernel<5>, grid, block, sm, ST(stream), (const uint16_t*)x, w, bias, (uint16_t*)y, sums, N, H, W, C, OH, OW, stride, pad_top, pad_left, dtype);
   return cobevt::check_launch("dwconv_swish");
 }
 
@@ -437,14 +455,14 @@ extern "C" int cobevt_se_gate(const float* sums, float inv_hw, const float* w1, 
                               const float* b2, float* gate, int32_t N, int32_t C, int32_t Cse, void* stream) {
   if (!sums || !w1 || !b1 || !w2 || !b2 || !gate || N <= 0 || C <= 0 || Cse <= 0 || (C + Cse) * 4 > 48 * 1024)
     return fail(COBEVT_ERR_SHAPE, "se_gate: bad args");
-  se_gate_kernel<<<N, 128, (size_t)(C + Cse) * sizeof(float), ST(stream)>>>(sums, inv_hw, w1, b1, w2, b2, gate, C, Cse);
+  cobevt::launch_k(se_gate_kernel, N, 128, (size_t)(C + Cse) * sizeof(float), ST(stream), sums, inv_hw, w1, b1, w2, b2, gate, C, Cse);
   return cobevt::check_launch("se_gate");
 }
 
 extern "C" int cobevt_scale_channels(const void* x, const float* gate, void* y, int32_t N, int64_t HW, int32_t C, int32_t dtype,
                                      void* stream) {
   if (!x || !gate || !y || C % 8) return fail(COBEVT_ERR_SHAPE, "scale_channels: bad args");
-  scale_channels_kernel<<<blocks_for((int64_t)N * HW * (C / 8), 256), 256, 0, ST(stream)>>>((const uint16_t*)x, gate, (uint16_t*)y, N, HW, C, dtype);
+  cobevt::launch_k(scale_channels_kernel, blocks_for((int64_t)N * HW * (C / 8), 256), 256, 0, ST(stream), (const uint16_t*)x, gate, (uint16_t*)y, N, HW, C, dtype);
   return cobevt::check_launch("scale_channels");
 }
 
@@ -452,9 +470,9 @@ extern "C" int cobevt_row_stats9(const void* x, const float* chan_tab, float* st
                                  void* stream) {
   if (!x || !chan_tab || !stats || rows <= 0 || (C != 32 && C != 64 && C != 128)) return fail(COBEVT_ERR_SHAPE, "row_stats9: bad args (C in {32,64,128})");
   const int64_t threads = rows * (C / 8);
-  if (C == 128) row_stats9_kernel<128><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
-  else if (C == 64) row_stats9_kernel<64><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
-  else row_stats9_kernel<32><<<blocks_for(threads, 256), 256, 0, ST(stream)>>>((const uint16_t*)x, chan_tab, stats, rows, dtype);
+  if (C == 128) cobevt::launch_k(row_stats9_kernel<128>, blocks_for(threads, 256), 256, 0, ST(stream), (const uint16_t*)x, chan_tab, stats, rows, dtype);
+  else if (C == 64) cobevt::launch_k(row_stats9_kernel<64>, blocks_for(threads, 256), 256, 0, ST(stream), (const uint16_t*)x, chan_tab, stats, rows, dtype);
+  else cobevt::launch_k(row_stats9_kernel<32>, blocks_for(threads, 256), 256, 0, ST(stream), (const uint16_t*)x, chan_tab, stats, rows, dtype);
   return cobevt::check_launch("row_stats9");
 }
 
@@ -471,9 +489,9 @@ extern "C" int cobevt_bev_q_analytic(const float* qx, int64_t x_rows, const floa
   if (cpb < tpb) cpb = tpb;
   if (cpb > 4096) cpb = 4096;
   dim3 grid((unsigned)((P + cpb - 1) / cpb), (unsigned)BL);
-  if (C == 128) bev_q_kernel<128><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
-  else if (C == 64) bev_q_kernel<64><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
-  else bev_q_kernel<32><<<grid, 256, 0, ST(stream)>>>(qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  if (C == 128) cobevt::launch_k(bev_q_kernel<128>, grid, 256, 0, ST(stream), qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  else if (C == 64) cobevt::launch_k(bev_q_kernel<64>, grid, 256, 0, ST(stream), qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
+  else cobevt::launch_k(bev_q_kernel<32>, grid, 256, 0, ST(stream), qx, x_rows, stats, world, chan_tab, E_inv, (uint16_t*)out, n, P, qa, qb, qd, ma, mb, eps, dtype, (int)cpb);
   return cobevt::check_launch("bev_q_analytic");
 }
 
@@ -485,6 +503,6 @@ extern "C" int cobevt_se_scale(void* x, const float* sums, float inv_hw, const f
   if (bpi < 1) bpi = 1;
   if (bpi > 1024) bpi = 1024;
   dim3 grid((unsigned)bpi, (unsigned)N);
-  se_scale_kernel<<<grid, 256, (size_t)(2 * C + Cse) * sizeof(float), ST(stream)>>>((uint16_t*)x, sums, inv_hw, w1, b1, w2, b2, HW, C, Cse, dtype);
+  cobevt::launch_k(se_scale_kernel, grid, 256, (size_t)(2 * C + Cse) * sizeof(float), ST(stream), (uint16_t*)x, sums, inv_hw, w1, b1, w2, b2, HW, C, Cse, dtype);
   return cobevt::check_launch("se_scale");
 }

@@ -16,6 +16,32 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 
 // ----------------------------------------------------------------------------
+// warp index the compiler can prove warp-uniform (the broadcast from lane 0): role selection, warpgroup ids, tile /
+// chunk counters and everything derived from them then live in UNIFORM registers instead of one vector register per
+// value.  In the attention kernel (112-register softmax threads) this removed every spill of the chunk loop.
+// -DCOBEVT_UNIFORM_WARP=0 builds the plain threadIdx.x >> 5 form (A/B timing).
+// ----------------------------------------------------------------------------
+#ifndef COBEVT_UNIFORM_WARP
+#define COBEVT_UNIFORM_WARP 1
+#endif
+__device__ __forceinline__ int warp_index_uniform() {
+#if COBEVT_UNIFORM_WARP
+  return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+#else
+  return (int)(threadIdx.x >> 5);
+#endif
+}
+
+// ----------------------------------------------------------------------------
+// programmatic dependent launch (see launch_k in common.h)
+// ----------------------------------------------------------------------------
+// pdl_trigger(): the next kernel of the stream may be scheduled once every CTA of this grid has executed it (or exited).
+// pdl_wait(): blocks until the previous kernel of the stream has completed and its memory is visible.  Both are no-ops
+// for a launch without the programmatic attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {

@@ -117,8 +117,10 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) token_mlp_kernel(const __grid_
   __shared__ __align__(16) float sB1[MLP_H], sB2[MLP_C], sGam[MLP_C], sBet[MLP_C];
 
   const CobevtMlpParams& p = a.p;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = warp_index_uniform();   // see sm100.cuh (-3 % on this kernel although ptxas reports 64 more spill bytes)
 
+  pdl_trigger();     // prologue + the 128 KB weight image load overlap the previous kernel's tail (see launch_k)
   if (tid == 0) {
     mbar_init(&w_full, 1);
     mbar_init(&a_full, 1);
@@ -155,6 +157,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) token_mlp_kernel(const __grid_
       mbar_arrive_expect_tx(&w_full, SW1_BYTES + SW2_BYTES);
       for (int i = 0; i < 4; ++i) bulk_g2s(sW1 + i * KBLK_BYTES, reinterpret_cast<const uint8_t*>(p.w1) + (size_t)i * KBLK_BYTES, KBLK_BYTES, &w_full);
       for (int i = 0; i < 4; ++i) bulk_g2s(sW2 + i * KBLK_BYTES, reinterpret_cast<const uint8_t*>(p.w2) + (size_t)i * KBLK_BYTES, KBLK_BYTES, &w_full);
+      pdl_wait();                                   // the token slabs are the previous kernel's output
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < a.m_tiles; tile += gridDim.x, ++it) {
         mbar_wait(&a_empty, (it & 1u) ^ 1u);
@@ -212,6 +215,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) token_mlp_kernel(const __grid_
   } else if (warp < 8) {
     // ======================================= team A: epilogue 1 ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MLP_REGS_EPI));
+    pdl_wait();
     const int q4 = warp & 3, hf = warp >> 2;                    // TMEM lane quarter, hidden-column half
     const int row = q4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
@@ -256,6 +260,7 @@ __global__ void __launch_bounds__(MLP_THREADS, 1) token_mlp_kernel(const __grid_
   } else {
     // ======================================= team B: epilogue 2 ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MLP_REGS_EPI));
+    pdl_wait();
     const int q4 = warp & 3, hf = (warp - 8) >> 2;              // TMEM lane quarter, output-column half
     const int row = q4 * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q4 * 32) << 16;
@@ -413,6 +418,6 @@ extern "C" int cobevt_token_mlp_fwd(const CobevtMlpParams* p, void* stream) {
   }
   const int sms = cobevt::num_sms();
   const int grid = a.m_tiles < sms ? a.m_tiles : sms;
-  kern<<<grid, MLP_THREADS, MLP_SMEM, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cobevt::launch_k(kern, grid, MLP_THREADS, MLP_SMEM, reinterpret_cast<cudaStream_t>(stream), a);
   return cobevt::check_launch("token_mlp_kernel");
 }

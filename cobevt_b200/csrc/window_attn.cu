@@ -112,6 +112,8 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b, int bf16) {
 }
 
 __global__ void __launch_bounds__(128, 2) window_attn_kernel(const __grid_constant__ AArgs a) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
@@ -393,6 +395,8 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // being processed), so the softmax threads never see a pipeline refill.
 template <bool BF16>
 __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __grid_constant__ AArgs a) {
+  pdl_trigger();
+  pdl_wait();
   // roles: warps 0-3 = softmax group 0, warps 4-7 = softmax group 1, warp 8 / 9 lane 0 = their MMA issuers
   // (warps 10, 11 only exist so that the issuers form a full warpgroup for setmaxnreg)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -410,7 +414,8 @@ __global__ void __launch_bounds__(V2_THREADS, 1) window_attn_v2_kernel(const __g
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = warp_index_uniform();                  // see sm100.cuh: keeps role / counter state in uniform registers
   const bool is_mma = warp >= 8;
   const int wg = is_mma ? warp - 8 : warp >> 2, wtid = tid & 127;
   int item = blockIdx.x;
@@ -879,8 +884,12 @@ constexpr int V3_POLY_DEFAULT = 0;     // measured: 0 / 25 % / 37.5 % within noi
 __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + SP3_BYTES); }
 
 // POLY: bit cc set -> the 8 exponentials of 8-key group cc (of the 8 groups of a 64-key chunk) use poly_exp2_pair
-template <bool BF16, int POLY>
+// QLIN: the four query rows a thread fetches per pass (rows r, r+32, r+64, r+96 of the tile) are a constant address step
+//       apart (one query plane per pass and 32 % window width == 0, decided on the host), so ONE offset is carried
+//       through the chunk loop instead of four -- the loop state of this kernel spills.
+template <bool BF16, int POLY, bool QLIN>
 __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __grid_constant__ AArgs a) {
+  pdl_trigger();   // barrier init and the TMEM allocation below may overlap the previous kernel's tail
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int n_ch = (a.Lk + CH3 - 1) / CH3;
@@ -901,7 +910,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   __shared__ uint32_t tmem_base_s;
 
   const CobevtAttnParams& p = a.p;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = warp_index_uniform();                  // see sm100.cuh: keeps role / counter state in uniform registers
   const bool is_mma = warp >= 4 * V3_WG;
   const int wg = is_mma ? warp - 4 * V3_WG : warp >> 2, wtid = tid & 127;
   int item = blockIdx.x;
@@ -921,6 +931,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     mbar_init(&bar_k, 1);
     mbar_init(&bar_v, 1);
     mbar_fence_init();
+    pdl_wait();
     if (a.kv_tma) {
       // the whole key window of every view is one strided box: 2 instructions instead of 16 B per thread
       const int X = win / a.k_ny, Y = win - X * a.k_ny;
@@ -935,6 +946,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
     tmem_alloc(&tmem_base_s, 512);
     tmem_relinquish();
   }
+  pdl_wait();                                               // Q, K, V, masks: outputs of earlier kernels
   const uint8_t* qb = reinterpret_cast<const uint8_t*>(p.q);
   const uint8_t* kb_ = reinterpret_cast<const uint8_t*>(p.k);
   const uint8_t* vb_ = reinterpret_cast<const uint8_t*>(p.v);
@@ -1094,37 +1106,52 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
 
     if (total > 0) {
     // ---- Q tiles (see the two-warpgroup kernel) -------------------------------------------------
-    uint32_t qoff16[4];
+    uint32_t qoff16[QLIN ? 1 : 4];
     const uint32_t plane16 = p.q_mean ? (uint32_t)(((int64_t)p.qmap.Hv * p.qmap.Wv * p.q_stride) >> 3) : 0u;
     const uint32_t q_dst = smem_u32(sQ);
-    int nq = 0, nq_pj = 0, nq_tile = t0;               // next pass whose Q has not been requested yet
-    auto issue_next_q = [&]() {
-      if (nq_pj == 0) {
+    // request the Q tile of pass Pn = pass pjn of tile `tile` (the caller derives both from the loop's own counters)
+    auto issue_q = [&](int Pn, int pjn, int tile) {
+      if (pjn == 0) {
+        if constexpr (QLIN) {
+          const int rr = tile * TILE_Q + (wtid >> 2);
+          const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, rr < rows_per_pass ? rr : 0);
+          const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
+          qoff16[0] = (uint32_t)(off >> 3) + (uint32_t)(wtid & 3);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = wtid + 128 * i;
-          const int r = idx >> 2, piece = idx & 3;
-          const int rr = nq_tile * TILE_Q + r;
-          qoff16[i] = 0xFFFFFFFFu;
-          if (rr < rows_per_pass) {
-            const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, rr);
-            const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
-            qoff16[i] = (uint32_t)(off >> 3) + piece;
+          for (int i = 0; i < 4; ++i) {
+            const int idx = wtid + 128 * i;
+            const int r = idx >> 2, piece = idx & 3;
+            const int rr = tile * TILE_Q + r;
+            qoff16[i] = 0xFFFFFFFFu;
+            if (rr < rows_per_pass) {
+              const Tok t = token_of(p.qmap, a.q_nx, a.q_ny, win, rr);
+              const int64_t off = ((((int64_t)b * p.qmap.views + t.n) * p.qmap.Hv + t.py) * p.qmap.Wv + t.px) * p.q_stride + head * DH;
+              qoff16[i] = (uint32_t)(off >> 3) + piece;
+            }
           }
         }
       }
-      const uint32_t view = split_pass ? (uint32_t)(sub + nq_pj * G) : (uint32_t)nq_pj;
-      const uint32_t dq = q_dst + (uint32_t)(nq & 1) * SQ_BYTES;
+      const uint32_t view = split_pass ? (uint32_t)(sub + pjn * G) : (uint32_t)pjn;
+      const uint32_t dq = q_dst + (uint32_t)(Pn & 1) * SQ_BYTES;
+      // QLIN: 32 tile rows further = 32 / w2 window rows further (x nx pixel rows for the dilated grid partition)
+      const uint32_t step16 = QLIN ? (uint32_t)(((32 / p.qmap.w2) * (p.qmap.grid ? a.q_nx : 1) * p.qmap.Wv * p.q_stride) >> 3) : 0u;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int idx = wtid + 128 * i;
-        const bool ok = qoff16[i] != 0xFFFFFFFFu;
-        const uint8_t* src = ok ? qb + ((size_t)(qoff16[i] + view * plane16) << 4) : qb;
+        bool ok;
+        uint32_t o16;
+        if constexpr (QLIN) {
+          ok = tile * TILE_Q + (idx >> 2) < rows_per_pass;
+          o16 = qoff16[0] + (uint32_t)i * step16;
+        } else {
+          ok = qoff16[i] != 0xFFFFFFFFu;
+          o16 = qoff16[i];
+        }
+        const uint8_t* src = ok ? qb + ((size_t)(o16 + view * plane16) << 4) : qb;
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dq + sw64_off(idx >> 2, idx & 3)), "l"(src), "r"(ok ? 16u : 0u) : "memory");
       }
       cp_async_commit();
-      ++nq;
-      if (++nq_pj == passes_per_tile) { nq_pj = 0; nq_tile += T; }
     };
     auto complete_q = [&](int Pn) {
       cp_async_wait<0>();
@@ -1210,11 +1237,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       tc_fence_before_sync();
     };
 
-    issue_next_q();
+    issue_q(0, 0, t0);
     complete_q(0);
     for (; g < total; ++g) {
       const bool q_now = (k == 0) && (P + 1 < NP);
-      if (q_now) issue_next_q();
+      if (q_now) {                                  // pass P + 1: the next view of this tile, or view 0 of the next tile
+        const bool wrap = pj + 1 == passes_per_tile;
+        issue_q(P + 1, wrap ? 0 : pj + 1, wrap ? q_tile + T : q_tile);
+      }
       const int key0 = (c_first + k * c_step) * CH3;
       mbar_wait_fast(bar_wg + BAR_S, (uint32_t)g & 1u);
       tc_fence_after_sync();
@@ -1422,6 +1452,8 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
 __global__ void attn_merge_kernel(const float* __restrict__ part, int S, int64_t seg_stride, uint16_t* __restrict__ out,
                                   CobevtTokenMap qmap, int nx, int ny, int B, int n_win, int heads, int Lq,
                                   int rows_per_pass, int passes, int q_mean, int out_stride, int bf16) {
+  pdl_trigger();
+  pdl_wait();
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t total = (int64_t)B * n_win * heads * rows_per_pass;
   if (idx >= total) return;
@@ -1533,17 +1565,23 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     if (p->part && !(smem <= 227 * 1024 && a.q_tiles >= 3))
       return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: key-segment mode needs a resident segment (<= 704 keys) and >= 3 query tiles");
     if (smem <= 227 * 1024 && (force_kernel != 2 || p->part)) {
-      static int attr_v3_dev[cobevt::kMaxDevices][4][2] = {};        // per device, per kernel instance
+      static int attr_v3_dev[cobevt::kMaxDevices][5][2] = {};        // per device, per kernel instance
       int* attr_v3 = nullptr;
       // share of the exponentials evaluated on the FMA pipes: COBEVT_ATTN_POLY = 0 none (default), 1 = 2/8, 2 = 3/8, 3 = 4/8
       static int poly_sel = -1;
       if (poly_sel < 0) { const char* e = getenv("COBEVT_ATTN_POLY"); poly_sel = e ? atoi(e) : V3_POLY_DEFAULT; if (poly_sel < 0 || poly_sel > 3) poly_sel = V3_POLY_DEFAULT; }
       typedef void (*KernT)(const AArgs);
-      static const KernT kerns[2][4] = {
-          {window_attn_v3_kernel<false, 0x00>, window_attn_v3_kernel<false, 0x44>, window_attn_v3_kernel<false, 0x92>, window_attn_v3_kernel<false, 0xAA>},
-          {window_attn_v3_kernel<true, 0x00>, window_attn_v3_kernel<true, 0x44>, window_attn_v3_kernel<true, 0x92>, window_attn_v3_kernel<true, 0xAA>}};
-      KernT kern = kerns[bf][poly_sel];
-      attr_v3 = attr_v3_dev[cobevt::current_device()][poly_sel];
+      static const KernT kerns[2][5] = {
+          {window_attn_v3_kernel<false, 0x00, false>, window_attn_v3_kernel<false, 0x44, false>, window_attn_v3_kernel<false, 0x92, false>,
+           window_attn_v3_kernel<false, 0xAA, false>, window_attn_v3_kernel<false, 0x00, true>},
+          {window_attn_v3_kernel<true, 0x00, false>, window_attn_v3_kernel<true, 0x44, false>, window_attn_v3_kernel<true, 0x92, false>,
+           window_attn_v3_kernel<true, 0xAA, false>, window_attn_v3_kernel<true, 0x00, true>}};
+      static int qlin_on = -1;          // COBEVT_ATTN_QLIN=0: always the four-offset instance (A/B timing)
+      if (qlin_on < 0) { const char* e = getenv("COBEVT_ATTN_QLIN"); qlin_on = (e && e[0] == '0') ? 0 : 1; }
+      const bool qlin = qlin_on && poly_sel == 0 && (p->q_mean || p->qmap.views == 1) && p->qmap.w2 > 0 && 32 % p->qmap.w2 == 0;
+      const int ksel = qlin ? 4 : poly_sel;
+      KernT kern = kerns[bf][ksel];
+      attr_v3 = attr_v3_dev[cobevt::current_device()][ksel];
       if (smem > attr_v3[bf]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
@@ -1574,7 +1612,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
         }
       }
       const int64_t ctas = (int64_t)p->B * a.n_win * p->heads * a.kv_segs;
-      kern<<<(unsigned)ctas, V3_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+      cobevt::launch_k(kern, (unsigned)ctas, V3_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), a);
       return cobevt::check_launch("window_attn_v3_kernel");
     }
   }
@@ -1594,7 +1632,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     }
     a.idesc_qk = make_idesc_f16(128, CH, bf, false, false);
     const int64_t ctas = (int64_t)p->B * a.n_win * p->heads;
-    kern<<<(unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+    cobevt::launch_k(kern, (unsigned)ctas, V2_THREADS, smem, reinterpret_cast<cudaStream_t>(stream), a);
     return cobevt::check_launch("window_attn_v2_kernel");
   }
   static bool attr_set_dev[cobevt::kMaxDevices] = {false};
@@ -1604,7 +1642,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "attn: set smem attr: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  window_attn_kernel<<<(unsigned)items, 128, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cobevt::launch_k(window_attn_kernel, (unsigned)items, 128, SMEM_BYTES, reinterpret_cast<cudaStream_t>(stream), a);
   return cobevt::check_launch("window_attn_kernel");
 }
 
@@ -1621,7 +1659,7 @@ extern "C" int cobevt_attn_merge(const float* part, int32_t segments, int64_t se
   const int rpp = q_mean ? qmap->w1 * qmap->w2 : Lq;
   if (out_stride == 0) out_stride = heads * DH;
   const int64_t total = (int64_t)B * n_win * heads * rpp;
-  attn_merge_kernel<<<(unsigned)((total + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+  cobevt::launch_k(attn_merge_kernel, (unsigned)((total + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream), 
       part, segments, segment_stride, reinterpret_cast<uint16_t*>(out), *qmap, nx, ny, B, n_win, heads, Lq, rpp, passes, q_mean,
       out_stride, dtype == COBEVT_BF16 ? 1 : 0);
   return cobevt::check_launch("attn_merge_kernel");
