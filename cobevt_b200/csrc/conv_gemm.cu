@@ -68,7 +68,9 @@ struct KArgs {
   int32_t dbg;                          // COBEVT_CONV_DEBUG bits (profiling experiments only): 1 no epilogue I/O, 2 no A loads, 4 no MMA
   uint32_t idesc;
   int32_t st_tma;                       // 16-bit outputs leave through per-warp smem tiles + TMA tensor stores
+  int32_t res_tma;                      // the 16-bit residual arrives through the same staging tiles by TMA tensor loads, one tile ahead
   alignas(64) CUtensorMap tmY, tmYln;   // output maps: {Cout, M} box {U, 32}  or  {Cout, OW, OH, N} box {U, 8, 4, 1}
+  alignas(64) CUtensorMap tmRes;        // residual map (same geometry as tmY) when res_tma
   alignas(64) CUtensorMap tmap;         // HALO: {C, W, H, N} box {64, 10, 18, 1}; LINEAR: {K, M} box {64, 128}; SWIZZLE_128B
 };
 
@@ -165,7 +167,8 @@ __device__ __forceinline__ void tmem_ld_unit(uint32_t taddr, uint32_t (&r)[U]) {
   }
 }
 
-template <int BN>
+// RT: residual by TMA (see the epilogue); a separate instance so that every other launch keeps its register allocation
+template <int BN, bool RT>
 __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_constant__ KArgs a) {
   constexpr int kBStage = BN * BLOCK_K * 2;
   constexpr int NACC = BN >= 256 ? 2 : 4;         // accumulator buffers in TMEM (power of two)
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
   uint8_t* sStage = sB + (a.resident_b ? a.KB * kBStage : SB * kBStage);   // 16 x STG_WARP_BYTES when a.st_tma
   __shared__ uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES], b_full[MAX_STAGES], b_empty[MAX_STAGES];
   __shared__ uint64_t acc_full[4], acc_empty[4], b_res_full;
+  __shared__ uint64_t res_full[16];               // per epilogue warp: its residual tile has landed in the staging buffer
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float sBias[512], sGamma[128], sBeta[128];
   __shared__ float2 sXch[2][2][2][128];           // [team][tile parity][column half][row] = (mean, M2)
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(&b_res_full, 1);
+    if (RT) for (int i = 0; i < 16; ++i) mbar_init(&res_full[i], 1);
     mbar_fence_init();
   }
   if (warp == 4) {
@@ -367,11 +372,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
     const int bf16 = p.dtype;
     const bool do_ln = p.y_ln != nullptr;      // host guarantees BN == Cout == 128 -> CW == U == 64
     uint32_t acc_it = 0;
+    // Residual by TMA (token GEMMs): the warp's 32 x 64 residual tile is requested into its staging buffer BEFORE the
+    // accumulator wait -- right after the previous tile's stores have left the buffer, i.e. about one tile ahead of its
+    // use -- so the epilogue reads it from shared memory instead of stalling on 8 global loads per thread after the wait
+    // (that stall was 25 % of this kernel's samples on the residual + LayerNorm GEMMs, profiles/r02_ncu_full.txt).
+    const bool res_tma = RT && active && !COBEVT_DBG(a, 9);
+    uint8_t* const stg_gen = sStage + (team * 8 + e) * STG_WARP_BYTES;
+    uint64_t* const res_bar = &res_full[team * 8 + e];
+    uint32_t res_par = 0;
     for (int tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++acc_it) {
       const int m_tile = tile / a.n_tiles;
       const int n_tile = tile - m_tile * a.n_tiles;
       const int buf = acc_it & (NACC - 1);
       if ((int)(acc_it % (uint32_t)n_teams) != team) continue;      // the other team's tile
+      if (RT && res_tma && lane == 0) {
+        bulk_wait_read0();                                          // the previous tile's stores have read the buffer
+        mbar_arrive_expect_tx(res_bar, 32 * U * 2);
+        tma_load_2d(stg_gen, &a.tmRes, res_bar, n_tile * BN + hf * CW, m_tile * BLOCK_M + q4 * 32);
+      }
       mbar_wait(&acc_full[buf], (acc_it / NACC) & 1);
       tc_fence_after_sync();
       if (!active) {
@@ -446,7 +464,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) conv_gemm_kernel(const __grid_
             v[j + 3] = __uint_as_float(r[j + 3]) + bb.w;
           }
         }
-        if (live && p.res) {
+        if (RT && res_tma) {
+          mbar_wait(res_bar, res_par);
+          res_par ^= 1u;
+          if constexpr (U == 64) {                   // the tile sits in the output map's SWIZZLE_128B image: this lane's row
+#pragma unroll
+            for (int ck = 0; ck < 8; ++ck) {
+              const uint4 rr = lds128(stg + (uint32_t)(lane * 128) + ((((uint32_t)ck ^ ((uint32_t)lane & 7u))) << 4));
+              const uint32_t w4[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+              for (int k2 = 0; k2 < 4; ++k2) {
+                const float2 f = unpack2(w4[k2], bf16);
+                v[ck * 8 + 2 * k2] += f.x;
+                v[ck * 8 + 2 * k2 + 1] += f.y;
+              }
+            }
+          }
+        } else if (live && p.res) {
           const uint8_t* rp = reinterpret_cast<const uint8_t*>(p.res) + (mr * p.Cout + n0) * 2;
 #pragma unroll
           for (int j0 = 0; j0 < U; j0 += 32) {
@@ -870,7 +904,7 @@ bool make_a_tmap(KArgs& a) {
 
 
 // output tensor maps for the TMA-store epilogue; U = columns per epilogue unit of this BN
-bool make_out_tmaps(KArgs& a, int U) {
+bool make_out_tmaps(KArgs& a, int U, bool single_unit) {
   cobevt::EncodeTiledFn enc = cobevt::get_encode_tiled();
   if (!enc) return false;
   const CobevtConvParams& p = a.p;
@@ -897,7 +931,15 @@ bool make_out_tmaps(KArgs& a, int U) {
     }
     return r == CUDA_SUCCESS;
   };
-  return one(&a.tmY, p.y) && one(&a.tmYln, p.y_ln);
+  if (!(one(&a.tmY, p.y) && one(&a.tmYln, p.y_ln))) return false;
+  // residual through the same tiles: plain [M][Cout] 16-bit residual of a single-unit (BN = 128) token GEMM
+  static int no_rt = -1;
+  if (no_rt < 0) { const char* e = getenv("COBEVT_CONV_NORESTMA"); no_rt = e ? atoi(e) : 0; }
+  a.res_tma = 0;
+  if (!no_rt && single_unit && p.res && p.res_rows == 0 && U == 64 && (a.mode == MODE_LINEAR || a.mode == MODE_GATHER) &&
+      one(&a.tmRes, const_cast<void*>(p.res)))
+    a.res_tma = 1;
+  return true;
 }
 
 template <int BN>
@@ -938,21 +980,27 @@ int launch(KArgs& a, cudaStream_t st) {
       fit = true;
     }
   }
-  if (a.st_tma && !make_out_tmaps(a, Uh)) {                 // no tensor maps: direct stores (the staging area stays unused)
+  a.res_tma = 0;
+  if (a.st_tma && !make_out_tmaps(a, Uh, BN == 128)) {      // no tensor maps: direct stores (the staging area stays unused)
     a.st_tma = 0;
+    a.res_tma = 0;
   }
   if (a.st_tma) smem += 16 * STG_WARP_BYTES;
   if (a.mode == MODE_PATCH && !a.resident_b) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "conv: PATCH mode needs the resident weight image");
-  static bool attr_set[cobevt::kMaxDevices] = {false};      // per device (and per BN: one static per instantiation)
+  static bool attr_set[cobevt::kMaxDevices][2] = {};         // per device and instance (and per BN: one static per instantiation)
   const int dev = cobevt::current_device();
-  if (!attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  void (*kern)(const KArgs) = conv_gemm_kernel<BN, false>;
+  if constexpr (BN == 128) {
+    if (a.res_tma) kern = conv_gemm_kernel<BN, true>;
+  }
+  if (!attr_set[dev][a.res_tma]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
     if (e != cudaSuccess) return cobevt::fail(COBEVT_ERR_CUDA, "conv: set smem attr: %s", cudaGetErrorString(e));
-    attr_set[dev] = true;
+    attr_set[dev][a.res_tma] = true;
   }
   const int num_sms = cobevt::num_sms();
   const int grid = a.total_tiles < num_sms ? a.total_tiles : num_sms;
-  cobevt::launch_k(conv_gemm_kernel<BN>, grid, NUM_THREADS, (size_t)smem, st, a);
+  cobevt::launch_k(kern, grid, NUM_THREADS, (size_t)smem, st, a);
   return cobevt::check_launch("conv_gemm_kernel");
 }
 
