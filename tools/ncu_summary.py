@@ -71,7 +71,7 @@ def cmd_traffic(specs):
         launches = []
         for r in rows:
             launches.append({"kernel": re.sub(r"\(.*", "", r[ki]).strip(), "dram_bytes": to_bytes(r[ir], units[ir]) + to_bytes(r[iw], units[iw]),
-                             "duration_us_under_ncu": float(r[it].replace(",", "")) * (1e-3 if units[it] == "ns" else 1.0)})
+                             "duration_us_under_ncu": float(r[it].replace(",", "")) * {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(units[it], 1.0)})
         tot = sum(l["dram_bytes"] for l in launches)
         out[fam] = {"dram_bytes_per_launch": tot / len(launches), "launches_captured": len(launches),
                     "algorithmic_bytes_per_launch": float(alg), "ratio": tot / len(launches) / float(alg),
