@@ -53,6 +53,7 @@ class AttnParams(ctypes.Structure):
         ("q_stride", c_i32), ("kv_stride", c_i32), ("out_stride", c_i32), ("q_mean", c_i32), ("scale", c_f32), ("dtype", c_i32),
         ("part", c_vp), ("kv_view0", c_i32), ("kv_views_total", c_i32), ("kv_segments", c_i32),
         ("part_segment_stride", ctypes.c_int64),
+        ("bias_layout", c_i32),
     ]
 
 

@@ -389,6 +389,23 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Volatile forms for the softmax inner loop of the four-warpgroup kernel: volatile asm statements keep their source
+// order, so the packing of key group cc-1 stays BETWEEN the exponentials of groups cc and cc+1.  Left to itself ptxas
+// sometimes hoists all 64 MUFU.EX2 of a chunk above every F2FP / STS (seen after an unrelated template change: +10 % on
+// the stage-0 attention), which puts the whole pack + store tail behind the last exponential.
+__device__ __forceinline__ float fast_exp2_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool BF16>
+__device__ __forceinline__ uint32_t pack2_v(float lo, float hi) {
+  uint32_t d;
+  if (BF16) asm volatile("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // The whole CTA is one continuous stream of 64-key chunks per warpgroup: chunk g = (pass P, chunk c)
 // where a "pass" is one (query tile, query view) pair.  The issuer runs two chunks ahead across pass
 // boundaries (the next pass' Q tile is prefetched into a second buffer while the current one is
@@ -887,7 +904,9 @@ __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * S
 // QLIN: the four query rows a thread fetches per pass (rows r, r+32, r+64, r+96 of the tile) are a constant address step
 //       apart (one query plane per pass and 32 % window width == 0, decided on the host), so ONE offset is carried
 //       through the chunk loop instead of four -- the loop state of this kernel spills.
-template <bool BF16, int POLY, bool QLIN>
+// BIAS: the additive-bias code (and the per-CTA chunk rotation that goes with it) exists only in the instances the
+//       biased attentions use; the unbiased launches keep their shorter chunk loop.
+template <bool BF16, int POLY, bool QLIN, bool BIAS>
 __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __grid_constant__ AArgs a) {
   pdl_trigger();   // barrier init and the TMEM allocation below may overlap the previous kernel's tail
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1019,6 +1038,16 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   const int passes_per_tile = split_pass ? (a.q_passes > sub ? (a.q_passes - sub + G - 1) / G : 0) : a.q_passes;
   const int n_uch = split_keys ? (n_ch > sub ? (n_ch - sub + G - 1) / G : 0) : n_ch;   // chunks per pass
   const int c_first = split_keys ? sub : 0, c_step = split_keys ? G : 1;
+  // Biased attentions: every CTA of a head reads the same dense bias, and CTAs launched together run in lockstep, so
+  // dozens of SMs ask the L2 for the same lines at the same moment (measured: the FuseBEVT attentions got SLOWER with
+  // the coalesced bias layout, which concentrates a warp's request on 4 lines).  Each CTA therefore walks its key
+  // chunks from a different starting chunk (the online softmax does not care about the order).
+  const int c_rot = (BIAS && n_uch > 1) ? (win + b) % n_uch : 0;
+  auto chunk_of = [&](int kk) {                               // step kk of a pass -> key chunk
+    int r = kk + c_rot;
+    if (r >= n_uch) r -= n_uch;
+    return c_first + r * c_step;
+  };
   const int NP = n_my_tiles * passes_per_tile;
   const int total = (COBEVT_DBG(a, 8) && wg > 0) ? 0 : NP * n_uch;
 
@@ -1053,7 +1082,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           tc_fence_after_sync();
         }
         const uint32_t qa = q_addr + (Pq & 1) * (SQ_BYTES / 16);
-        const uint32_t kb = k_addr + (c_first + kq * c_step) * (CH3 * 64 / 16);
+        const uint32_t kb = k_addr + chunk_of(kq) * (CH3 * 64 / 16);
         if (elect_one()) {
 #pragma unroll
           for (int ks = 0; ks < DH / 16; ++ks)
@@ -1075,7 +1104,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         if (g == 0 && a.kv_tma) mbar_wait(&bar_v, 0);               // the V window has landed
         tc_fence_after_sync();
         {                                                           // O (+)= P(g) V(chunk)
-          const uint32_t va = v_addr + (c_first + k * c_step) * (CH3 * 64 / 16);
+          const uint32_t va = v_addr + chunk_of(k) * (CH3 * 64 / 16);
           if (elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < CH3 / 16; ++ks)
@@ -1245,7 +1274,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
         const bool wrap = pj + 1 == passes_per_tile;
         issue_q(P + 1, wrap ? 0 : pj + 1, wrap ? q_tile + T : q_tile);
       }
-      const int key0 = (c_first + k * c_step) * CH3;
+      const int key0 = chunk_of(k) * CH3;
       mbar_wait_fast(bar_wg + BAR_S, (uint32_t)g & 1u);
       tc_fence_after_sync();
       float x[CH3];
@@ -1260,7 +1289,7 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       tc_fence_before_sync();
       mbar_arrive_a(bar_wg + BAR_F);                // S(g) sits in registers: its TMEM columns are free
       const bool use_km = any_mask || (key0 + CH3 > a.Lk);
-      const bool plain = !use_km && !(p.bias != nullptr);
+      const bool plain = !use_km && !BIAS;
       float cmax;                                   // chunk max, log2 domain
       if (plain) {
         float mr[4] = {x[0], x[1], x[2], x[3]};
@@ -1280,7 +1309,21 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           for (int j = 0; j < CH3; j += 2) fmul2(x[j], x[j + 1], x[j], x[j + 1], sl2, sl2);
         }
         const int qrow = q_tile * TILE_Q + wtid;
-        if (p.bias && qrow < rows_per_pass) {
+        if (BIAS && p.bias_layout == 1 && qrow < rows_per_pass) {
+          // key-group-major bias (heads, Lk/4, Lq, 4): lane = query row, so one load instruction of the warp covers 512
+          // contiguous bytes (4 L1 wavefronts) instead of 32 rows 4 x Lk bytes apart (32 wavefronts) -- the row-major
+          // form made the biased attentions L1-wavefront bound (2.2 us per 64-key chunk step)
+          const float4* bp4 = reinterpret_cast<const float4*>(p.bias) +
+                              ((int64_t)head * (a.bias_ld >> 2) + ((bias_k0 + key0) >> 2)) * a.Lq + qrow;
+#pragma unroll
+          for (int j = 0; j < CH3 / 4; ++j) {
+            if (key0 + 4 * j < a.Lk) {
+              const float4 b4 = __ldg(bp4 + (int64_t)j * a.Lq);
+              ffma2(x[4 * j + 0], x[4 * j + 1], b4.x, b4.y, L2E, L2E, x[4 * j + 0], x[4 * j + 1]);
+              ffma2(x[4 * j + 2], x[4 * j + 3], b4.z, b4.w, L2E, L2E, x[4 * j + 2], x[4 * j + 3]);
+            }
+          }
+        } else if (BIAS && qrow < rows_per_pass) {
           const float* bp = p.bias + ((int64_t)head * a.Lq + qrow) * a.bias_ld + bias_k0 + key0;
           if (bias_vec && key0 + CH3 <= a.Lk) {
 #pragma unroll
@@ -1328,6 +1371,14 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
       const float nm = -m_run;
       const float es = plain ? sl2 : 1.0f;
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[CH3 / 2];                         // P in 16 bits, packed one key group behind the exponentials
+      auto pack_group = [&](int cc) {
+        const int j = cc * 8;
+        pk[cc * 4 + 0] = pack2_v<BF16>(x[j + 0], x[j + 1]);
+        pk[cc * 4 + 1] = pack2_v<BF16>(x[j + 2], x[j + 3]);
+        pk[cc * 4 + 2] = pack2_v<BF16>(x[j + 4], x[j + 5]);
+        pk[cc * 4 + 3] = pack2_v<BF16>(x[j + 6], x[j + 7]);
+      };
 #pragma unroll
       for (int cc = 0; cc < CH3 / 8; ++cc) {
         const int j = cc * 8;
@@ -1340,22 +1391,20 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
           for (int t = 0; t < 8; t += 2) poly_exp2_pair(x[j + t], x[j + t + 1]);
         } else {
 #pragma unroll
-          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2(x[j + t]);
+          for (int t = 0; t < 8; ++t) x[j + t] = fast_exp2_v(x[j + t]);
         }
+        if (cc >= 1) pack_group(cc - 1);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j], x[j + 1]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 2], x[j + 3]);
         fadd2(sm[0], sm[1], sm[0], sm[1], x[j + 4], x[j + 5]);
         fadd2(sm[2], sm[3], sm[2], sm[3], x[j + 6], x[j + 7]);
       }
+      pack_group(CH3 / 8 - 1);
       // the P buffer (and O) are free once P V of the previous chunk has landed
       if (g >= 1) mbar_wait_fast(bar_wg + BAR_O, (uint32_t)(g - 1) & 1u);
 #pragma unroll
-      for (int cc = 0; cc < CH3 / 8; ++cc) {
-        const int j = cc * 8;
-        sts128(p_swz ^ ((uint32_t)cc << 4),
-               pack2<BF16>(x[j + 0], x[j + 1]), pack2<BF16>(x[j + 2], x[j + 3]),
-               pack2<BF16>(x[j + 4], x[j + 5]), pack2<BF16>(x[j + 6], x[j + 7]));
-      }
+      for (int cc = 0; cc < CH3 / 8; ++cc)
+        sts128(p_swz ^ ((uint32_t)cc << 4), pk[cc * 4 + 0], pk[cc * 4 + 1], pk[cc * 4 + 2], pk[cc * 4 + 3]);
       l_run += (sm[0] + sm[1]) + (sm[2] + sm[3]);
       if (q_now) complete_q(P + 1);
       // ---- a new pass overwrites O: the finished one has to leave TMEM first ----------------------
@@ -1550,6 +1599,10 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   if (a.p.q_stride < a.C || a.p.kv_stride < a.C || a.p.out_stride < a.C || (a.p.q_stride | a.p.kv_stride | a.p.out_stride) % 8)
     return cobevt::fail(COBEVT_ERR_SHAPE, "attn: token strides must be >= heads*32 and multiples of 8");
   if (p->bias && p->q_mean) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: bias with q_mean");
+  if (p->bias_layout != 0 && p->bias_layout != 1) return cobevt::fail(COBEVT_ERR_SHAPE, "attn: bias_layout must be 0 or 1");
+  const bool bias_kq = p->bias && p->bias_layout == 1;
+  if (bias_kq && (((a.Lk | a.bias_ld | (km.w1 * km.w2)) & 3) != 0))
+    return cobevt::fail(COBEVT_ERR_SHAPE, "attn: key-group-major bias needs key counts that are multiples of 4");
   if (p->part && !p->out) {}   // (out is ignored in key-segment mode)
   if (p->dtype != COBEVT_F16 && p->dtype != COBEVT_BF16) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: dtype");
   const bool bf = p->dtype == COBEVT_BF16;
@@ -1565,21 +1618,26 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
     if (p->part && !(smem <= 227 * 1024 && a.q_tiles >= 3))
       return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: key-segment mode needs a resident segment (<= 704 keys) and >= 3 query tiles");
     if (smem <= 227 * 1024 && (force_kernel != 2 || p->part)) {
-      static int attr_v3_dev[cobevt::kMaxDevices][5][2] = {};        // per device, per kernel instance
+      static int attr_v3_dev[cobevt::kMaxDevices][6][2] = {};        // per device, per kernel instance
       int* attr_v3 = nullptr;
       // share of the exponentials evaluated on the FMA pipes: COBEVT_ATTN_POLY = 0 none (default), 1 = 2/8, 2 = 3/8, 3 = 4/8
       static int poly_sel = -1;
       if (poly_sel < 0) { const char* e = getenv("COBEVT_ATTN_POLY"); poly_sel = e ? atoi(e) : V3_POLY_DEFAULT; if (poly_sel < 0 || poly_sel > 3) poly_sel = V3_POLY_DEFAULT; }
       typedef void (*KernT)(const AArgs);
-      static const KernT kerns[2][5] = {
-          {window_attn_v3_kernel<false, 0x00, false>, window_attn_v3_kernel<false, 0x44, false>, window_attn_v3_kernel<false, 0x92, false>,
-           window_attn_v3_kernel<false, 0xAA, false>, window_attn_v3_kernel<false, 0x00, true>},
-          {window_attn_v3_kernel<true, 0x00, false>, window_attn_v3_kernel<true, 0x44, false>, window_attn_v3_kernel<true, 0x92, false>,
-           window_attn_v3_kernel<true, 0xAA, false>, window_attn_v3_kernel<true, 0x00, true>}};
-      static int qlin_on = -1;          // COBEVT_ATTN_QLIN=0: always the four-offset instance (A/B timing)
-      if (qlin_on < 0) { const char* e = getenv("COBEVT_ATTN_QLIN"); qlin_on = (e && e[0] == '0') ? 0 : 1; }
-      const bool qlin = qlin_on && poly_sel == 0 && (p->q_mean || p->qmap.views == 1) && p->qmap.w2 > 0 && 32 % p->qmap.w2 == 0;
-      const int ksel = qlin ? 4 : poly_sel;
+      static const KernT kerns[2][6] = {
+          {window_attn_v3_kernel<false, 0x00, false, false>, window_attn_v3_kernel<false, 0x44, false, false>,
+           window_attn_v3_kernel<false, 0x92, false, false>, window_attn_v3_kernel<false, 0xAA, false, false>,
+           window_attn_v3_kernel<false, 0x00, true, false>, window_attn_v3_kernel<false, 0x00, false, true>},
+          {window_attn_v3_kernel<true, 0x00, false, false>, window_attn_v3_kernel<true, 0x44, false, false>,
+           window_attn_v3_kernel<true, 0x92, false, false>, window_attn_v3_kernel<true, 0xAA, false, false>,
+           window_attn_v3_kernel<true, 0x00, true, false>, window_attn_v3_kernel<true, 0x00, false, true>}};
+      // COBEVT_ATTN_QLIN=1 selects the single-offset instance.  Off by default: it was 0.7 % faster when introduced, but
+      // since the bias code moved into its own instance ptxas hoists all 64 MUFU.EX2 of a chunk above the pack / store
+      // tail in THIS instance only (+10 % on the stage-0 attention, profiles/r02g_attn_bias_ab.log)
+      static int qlin_on = -1;
+      if (qlin_on < 0) { const char* e = getenv("COBEVT_ATTN_QLIN"); qlin_on = (e && e[0] == '1') ? 1 : 0; }
+      const bool qlin = qlin_on && poly_sel == 0 && !p->bias && (p->q_mean || p->qmap.views == 1) && p->qmap.w2 > 0 && 32 % p->qmap.w2 == 0;
+      const int ksel = p->bias ? 5 : (qlin ? 4 : poly_sel);
       KernT kern = kerns[bf][ksel];
       attr_v3 = attr_v3_dev[cobevt::current_device()][ksel];
       if (smem > attr_v3[bf]) {
@@ -1618,6 +1676,7 @@ extern "C" int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream) {
   }
   if (p->kv_view0 != 0 || a.kv_vt != km.views || a.kv_segs > 1)
     return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: a K/V view subset needs the resident four-warpgroup kernel (<= 704 keys)");
+  if (bias_kq) return cobevt::fail(COBEVT_ERR_UNSUPPORTED, "attn: key-group-major bias needs the resident four-warpgroup kernel (<= 704 keys per call)");
   if (a.Lk <= KV_CAP_KEYS) {
     const int keys_pad = cobevt::ceil_div(a.Lk, CH) * CH;
     a.q_dbuf = (v2_fixed_smem(1) + keys_pad * (128 + 4) <= 227 * 1024) ? 1 : 0;

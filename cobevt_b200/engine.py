@@ -284,7 +284,7 @@ class GlobalAttnPlan:
         self.out = PackedConv(m.to_out[0].weight.detach().float(), None, device, dtype)
         self.heads, self.scale = m.heads, m.scale
         bias = m.rel_pos_bias.weight.detach().float()[m.rel_pos_indices.to(m.rel_pos_bias.weight.device)]  # T T h
-        self.bias = bias.permute(2, 0, 1).contiguous().to(device)
+        self.bias = ops.AttnBias(bias.permute(2, 0, 1).contiguous().to(device))
 
     def run(self, x):
         BL, H, W, d = x.shape
@@ -334,7 +334,7 @@ class SwapAttnPlan:
         self.out = PackedConv(at.to_out[0].weight.detach().float(), None, device, dtype)
         tbl = at.relative_position_bias_table.weight.detach().float()
         idx = at.relative_position_index.to(tbl.device)
-        self.bias = tbl[idx].permute(2, 0, 1).contiguous().to(device)      # heads T T
+        self.bias = ops.AttnBias(tbl[idx].permute(2, 0, 1).contiguous().to(device))      # heads T T
         self.heads, self.scale = at.heads, at.scale
         ff = prenorm_ffd.fn.net
         self.ff = PackedMlp(*fold_ln_linear(prenorm_ffd.norm, ff[0]), ff[3].weight.detach().float(),

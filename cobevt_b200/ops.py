@@ -4,6 +4,7 @@ Tensors are device buffers only (torch is plumbing: allocation + streams).  Ever
 raises on a non-zero return code; nothing here computes on the host or falls back.
 """
 import ctypes
+import os
 
 import torch
 
@@ -252,6 +253,20 @@ def _resident_keys():
     return _RESIDENT_KEYS
 
 
+class AttnBias:
+    """A constant additive attention bias (heads, Lq, Lk) fp32, held in both layouts the kernels read: row-major, and
+    key-group-major (heads, Lk/4, Lq, 4) for the resident-key kernel (a warp's 32 query rows then read 512 contiguous
+    bytes per key group).  Built once per plan; `window_attention` picks the layout."""
+
+    def __init__(self, bias):
+        assert bias.dtype == torch.float32 and bias.dim() == 3
+        self.raw = bias.contiguous()
+        h, lq, lk = bias.shape
+        self.kq = None
+        if lk % 4 == 0 and os.environ.get("COBEVT_ATTN_BIAS_KQ", "1") != "0":      # =0: row-major only (A/B timing)
+            self.kq = self.raw.view(h, lq, lk // 4, 4).permute(0, 2, 1, 3).contiguous()
+
+
 def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_pad=None,
                      bias=None, key_mask=None):
     """q: (B, qviews, Hq, Wq, C); k, v: (B, kviews, Hk, Wk, C) 16-bit contiguous (valid extents).
@@ -282,6 +297,9 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p = AttnParams()
     p.q, p.k, p.v, p.out = _ptr(q), _ptr(k), _ptr(v), _ptr(out)
     p.k_pad, p.v_pad = _ptr(k_pad), _ptr(v_pad)
+    bias_kq = None
+    if isinstance(bias, AttnBias):
+        bias, bias_kq = bias.raw, bias.kq
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.is_contiguous()
     if key_mask is not None:
@@ -291,6 +309,12 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
     p.B, p.heads, p.q_mean, p.scale, p.dtype = B, heads, 1 if q_mean else 0, scale, dtype_code(q.dtype)
     p.q_stride, p.kv_stride, p.out_stride = qs, ks, C
     label = f"B={B} win={n_win} heads={heads} Lq={lq} Lk={lk} mean={int(bool(q_mean))} bias={bias is not None}"
+
+    def use_kq(pp, keys_per_call, keys_per_view):
+        # the key-group-major copy serves the resident-key kernel only (see include/cobevt_b200.h, bias_layout)
+        if bias_kq is not None and keys_per_call <= _resident_keys() and keys_per_view % 4 == 0:
+            pp.bias, pp.bias_layout = _ptr(bias_kq), 1
+
     # windows whose keys do not fit one resident pass: one call per group of K/V views (each a resident segment
     # of the four-warpgroup kernel) + a log-sum-exp merge; e.g. the stage-2 global cross attention, 6 x 420 keys
     per_view = kvmap.w1 * kvmap.w2
@@ -312,6 +336,7 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
         ps.kvmap = token_map(vps, kvmap.H, kvmap.W, kvmap.w1, kvmap.w2, bool(kvmap.grid))
         ps.out = None
         ps.kv_view0, ps.kv_views_total, ps.kv_segments = 0, kvmap.views, nseg
+        use_kq(ps, vps * per_view, per_view)
         nbytes = int(_lib.lib().cobevt_attn_workspace_bytes(ctypes.byref(ps)))      # the library sizes its own scratch
         assert nbytes == nseg * B * n_win * heads * lq * 36 * 4, nbytes
         part = torch.empty((nseg, nbytes // (4 * nseg)), dtype=torch.float32, device=q.device)
@@ -323,6 +348,7 @@ def window_attention(q, k, v, qmap, kvmap, heads, scale, q_mean, k_pad=None, v_p
                                                     ctypes.byref(qmap), B, heads, 1 if q_mean else 0, C,
                                                     dtype_code(q.dtype), _stream()), "cobevt_attn_merge")
         return out
+    use_kq(p, lk, per_view)
     with _timed("window_attn", 4 * B * n_win * heads * lq * lk * 32, label):
         _lib.check(_lib.lib().cobevt_window_attn_fwd(ctypes.byref(p), _stream()), "cobevt_window_attn_fwd")
     return out

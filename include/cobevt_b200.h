@@ -147,6 +147,9 @@ typedef struct {
   int32_t kv_segments;    /* 0/1: one segment; n: ONE launch covers n consecutive segments of kvmap.views views
                              each (starting at kv_view0), segment s writing to part + s * part_segment_stride */
   int64_t part_segment_stride; /* in floats */
+  int32_t bias_layout;    /* 0: bias is (heads, Lq, Lk) row-major.  1: key-group-major (heads, Lk/4, Lq, 4): the 32 query rows
+                             of a warp read 512 contiguous bytes per key group instead of 32 scattered 16-byte pieces
+                             (resident-key kernel only: Lk per call <= cobevt_attn_resident_keys(), Lk % 4 == 0)        */
 } CobevtAttnParams;
 
 int cobevt_window_attn_fwd(const CobevtAttnParams* p, void* stream);

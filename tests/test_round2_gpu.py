@@ -407,3 +407,35 @@ def test_bev_q_analytic_vs_direct(C, shared, n):
     ref = F.layer_norm(y, (C,)) @ wq.half().float().T + bq
     assert got.shape == ref.shape
     assert relerr(got, ref) < 2e-3, relerr(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,L", [(False, 5), (True, 3)])
+def test_attention_bias_layouts_agree(grid, L):
+    """The key-group-major bias copy (ops.AttnBias, bias_layout 1) only changes how the resident-key kernel addresses the
+    bias: window / grid self-attention with bias + mask and the two-segment global attention must be bit-identical to the
+    row-major call."""
+    from cobevt_b200 import ops
+    torch.manual_seed(11)
+    H = W = 32
+    w, heads, C, B = 8, 4, 128, 2
+    T = L * w * w
+    qkv = torch.randn(B, L, H, W, 3 * C).cuda().half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    bias = (torch.randn(heads, T, T) * 0.5).cuda()
+    mask = (torch.rand(B, H, W, L) > 0.3).to(torch.uint8).cuda()
+    mask[..., 0] = 1
+    tm = ops.token_map(L, H, W, w, w, grid)
+    a = ops.window_attention(q, k, v, tm, tm, heads, 32 ** -0.5, False, bias=bias, key_mask=mask)
+    b = ops.window_attention(q, k, v, tm, tm, heads, 32 ** -0.5, False, bias=ops.AttnBias(bias), key_mask=mask)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
+    # global: one 32 x 32 plane that is the window, 1024 keys = two resident segments with a key offset into the bias rows
+    qkv = torch.randn(B, 1, 32, 32, 3 * C).cuda().half()
+    q, k, v = qkv[..., :C], qkv[..., C:2 * C], qkv[..., 2 * C:]
+    bias = (torch.randn(heads, 1024, 1024) * 0.5).cuda()
+    tm = ops.token_map(1, 32, 32, 32, 32, False)
+    a = ops.window_attention(q, k, v, tm, tm, heads, 32 ** -0.5, False, bias=bias)
+    b = ops.window_attention(q, k, v, tm, tm, heads, 32 ** -0.5, False, bias=ops.AttnBias(bias))
+    torch.cuda.synchronize()
+    assert torch.equal(a, b)
