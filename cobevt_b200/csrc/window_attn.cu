@@ -1042,7 +1042,9 @@ __global__ void __launch_bounds__(V3_THREADS, 1) window_attn_v3_kernel(const __g
   // dozens of SMs ask the L2 for the same lines at the same moment (measured: the FuseBEVT attentions got SLOWER with
   // the coalesced bias layout, which concentrates a warp's request on 4 lines).  Each CTA therefore walks its key
   // chunks from a different starting chunk (the online softmax does not care about the order).
-  const int c_rot = (BIAS && n_uch > 1) ? (win + b) % n_uch : 0;
+  // (the start chunk depends on the window only -- never on the batch row -- so a sample's bits do not depend on its
+  //  slot in the batch: the N-rank shard check compares bit for bit)
+  const int c_rot = (BIAS && n_uch > 1) ? win % n_uch : 0;
   auto chunk_of = [&](int kk) {                               // step kk of a pass -> key chunk
     int r = kk + c_rot;
     if (r >= n_uch) r -= n_uch;
