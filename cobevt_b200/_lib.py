@@ -92,6 +92,14 @@ def lib():
             fn = getattr(L, name)
             fn.restype = ctypes.c_int
             fn.argtypes = argt
+        # the ctypes declarations above must describe the structs exactly as the library was compiled
+        L.cobevt_struct_bytes.restype = ctypes.c_int32
+        L.cobevt_struct_bytes.argtypes = [c_i32]
+        for which, cls in enumerate((ConvParams, AttnParams, MlpParams, TokenMap)):
+            want = int(L.cobevt_struct_bytes(which))
+            if want != ctypes.sizeof(cls):
+                raise RuntimeError(f"{LIB_PATH}: sizeof({cls.__name__}) is {want} in the library but {ctypes.sizeof(cls)} "
+                                   "in cobevt_b200/_lib.py -- rebuild the library (cobevt_b200/csrc/build.sh)")
         _lib = L
     return _lib
 
@@ -133,6 +141,6 @@ def check(rc, what):
 
 
 EXPORTED_SYMBOLS = [
-    "cobevt_version", "cobevt_last_error", "cobevt_conv_packed_bytes",
+    "cobevt_version", "cobevt_last_error", "cobevt_struct_bytes", "cobevt_conv_packed_bytes",
     "cobevt_conv_pack_weight", "cobevt_conv2d_nhwc_fwd", "cobevt_token_mlp_fwd", "cobevt_window_attn_fwd", "cobevt_attn_merge", "cobevt_attn_resident_keys", "cobevt_attn_workspace_bytes",
 ] + list(_ELTWISE_SIGS)

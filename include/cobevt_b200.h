@@ -33,6 +33,9 @@ enum { COBEVT_ACT_NONE = 0, COBEVT_ACT_RELU = 1, COBEVT_ACT_GELU = 2, COBEVT_ACT
 
 int cobevt_version(void);
 const char* cobevt_last_error(void);
+/* sizeof of a parameter struct in this build: 0 CobevtConvParams, 1 CobevtAttnParams, 2 CobevtMlpParams, 3 CobevtTokenMap
+ * (-1 otherwise).  Bindings check their own declarations against it once, at load time (cobevt_b200/_lib.py does). */
+int32_t cobevt_struct_bytes(int32_t which);
 
 /* ---------------------------------------------------------------------------
  * Implicit-GEMM convolution / token GEMM on tcgen05 tensor cores.

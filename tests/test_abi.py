@@ -37,6 +37,35 @@ def test_version_and_error_string():
     assert L.cobevt_window_attn_fwd(ctypes.byref(a), None) == -1
 
 
+def test_struct_layouts_match_the_library():
+    """ctypes declarations vs the structs as compiled (cobevt_struct_bytes); field offsets the kernels rely on follow from
+    the declaration order, so the sizes pin accidental drift (the loader refuses a mismatching library as well)."""
+    from cobevt_b200 import _lib
+    L = _lib.lib()
+    for which, cls in enumerate((_lib.ConvParams, _lib.AttnParams, _lib.MlpParams, _lib.TokenMap)):
+        assert L.cobevt_struct_bytes(which) == ctypes.sizeof(cls), cls.__name__
+    assert L.cobevt_struct_bytes(99) == -1
+    assert _lib.AttnParams.bias_layout.offset + 4 <= ctypes.sizeof(_lib.AttnParams)
+    a = _lib.AttnParams()
+    a.bias_layout = 7                                           # rejected on the host before anything else is read
+    a.q = a.k = a.v = a.out = ctypes.c_void_p(256)
+    assert L.cobevt_window_attn_fwd(ctypes.byref(a), None) == -1
+
+
+def test_attn_bias_key_group_major_copy():
+    """ops.AttnBias: kq[h, k/4, q, :] == raw[h, q, 4*(k/4) : 4*(k/4)+4] (the layout bias_layout = 1 addresses)."""
+    import torch
+    from cobevt_b200 import ops
+    raw = torch.arange(2 * 6 * 8, dtype=torch.float32).reshape(2, 6, 8)
+    b = ops.AttnBias(raw)
+    assert b.kq.shape == (2, 2, 6, 4) and b.kq.is_contiguous()
+    for h in range(2):
+        for q in range(6):
+            for g in range(2):
+                assert torch.equal(b.kq[h, g, q], raw[h, q, 4 * g:4 * g + 4])
+    assert ops.AttnBias(torch.zeros(1, 3, 6)).kq is None       # key count not a multiple of 4: row-major only
+
+
 def test_attention_host_validation_and_capacity():
     """Host-side checks of the attention entry points (no kernel is launched: every call fails validation)."""
     from cobevt_b200 import _lib
