@@ -897,7 +897,8 @@ constexpr int V3_WG = 4;
 constexpr int V3_THREADS = (V3_WG + 1) * 128;            // 640
 constexpr int V3_REGS_SOFTMAX = 112, V3_REGS_ISSUER = 32;   // the CTA pool is 640 x 96 = 61440 = 16*32*112 + 4*32*32
 constexpr int SP3_BYTES = TILE_Q * CH3 * 2;              // 16 KB: one P buffer per warpgroup
-constexpr int V3_POLY_DEFAULT = 0;     // measured: 0 / 25 % / 37.5 % within noise, 50 % slower (profiles/r02_attn_ab.log)
+constexpr int V3_POLY_DEFAULT = 1;     // 2 of 8 key groups.  Null result while the chunk loop still spilled (profiles/r02_attn_ab.log);
+                                       // with the MUFU queue as the top stall: attention family 3183 -> 3077 us (profiles/r02g_attn_bias_ab.log)
 __host__ __device__ constexpr int v3_fixed_smem() { return 1024 + V3_WG * (2 * SQ_BYTES + SP3_BYTES); }
 
 // POLY: bit cc set -> the 8 exponentials of 8-key group cc (of the 8 groups of a 64-key chunk) use poly_exp2_pair
