@@ -16,6 +16,12 @@
 //                  and the tcgen05.commit that frees stages / publishes accumulators
 //   warps 18-19    idle (they complete the control warpgroup for setmaxnreg: 104 registers for the 16 workers)
 //
+// Instances: conv_gemm_kernel<BN, RT>.  RT = true (BN = 128 token GEMMs with a plain 16-bit residual): the residual tile
+// of a warp arrives in its staging buffer by TMA one tile ahead instead of by per-thread loads after the accumulator wait.
+// All kernels are launched with programmatic dependent launch (common.h launch_k): prologue and resident weights are
+// fetched before griddepcontrol.wait, activations only after it.  The warp index is broadcast from lane 0
+// (sm100.cuh warp_index_uniform) so that role / tile state lives in uniform registers.
+//
 // A-operand modes (host-selected, see cobevt_conv2d_nhwc_fwd)
 //   HALO    3x3 / stride 1 / pad 1 / Cin % 64 == 0 (the bulk of the ResNet encoder): the output tile is 16 rows x 8
 //           pixels; its 18 x 10 x 64ch input halo is ONE TMA box per 64-channel slab and all nine taps read it in

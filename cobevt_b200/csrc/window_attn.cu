@@ -14,7 +14,13 @@
 //   window_attn_kernel      anything longer: K/V streamed in 128-key chunks, one 128-thread CTA per query tile.
 //
 // Per chunk:  S = Q K^T (tcgen05.mma) -> TMEM -> registers (tcgen05.ld); online softmax in fp32 with exp2 on the
-// MUFU (scale * log2 e folded); P -> shared memory; O (+)= P V (tcgen05.mma).
+// MUFU (scale * log2 e folded; by default two of the eight key groups of a chunk use the FMA-pipe polynomial instead);
+// P -> shared memory; O (+)= P V (tcgen05.mma).
+//
+// window_attn_v3_kernel<BF16, POLY, QLIN, BIAS> instances: unbiased launches run <., 0x44, false, false>; the biased ones
+// (FuseBEVT, global self-attention) run <., 0, false, true>, the only instance with the bias code: it reads the
+// key-group-major bias copy (bias_layout 1) and starts its key-chunk walk at chunk (window % chunks) so that the CTAs of
+// a head do not hammer the same L2 lines.  QLIN (one carried query offset) is kept behind COBEVT_ATTN_QLIN=1.
 //
 // Reference: CrossWinAttention.forward fax_modules.py:198-248, partitions
 // fax_modules.py:399-433; Attention.forward fax_modules.py:132-176;
